@@ -1,0 +1,463 @@
+"""Host-side mirror of the GeoStatsModels.jl interface for the interpolation hot path.
+
+Same names, argument meaning and error behaviour as the reference (paths under /root/reference/src):
+``fit`` (models.jl:38), ``predict`` (models.jl:54-61), ``predictprob`` (models.jl:69-76), ``status``
+(models.jl:84), ``fitpredict`` (models.jl:102-129) and the models ``IDW`` (idw.jl:20-26),
+``SimpleKriging`` (krig/simple.jl:29-45), ``OrdinaryKriging`` (krig/ordinary.jl:25-27),
+``UniversalKriging`` (krig/universal.jl:45-50), ``Kriging`` (krig.jl:423-427) with
+Gaussian/Spherical/Exponential variograms.  Julia is not installed in this image, so this Python layer
+stands where the Julia shim of INTEGRATION.md would: it does the orchestration of models.jl (point
+support, `_scale`, neighbour-limit clamping) and hands whole target domains to the C ABI.
+Everything numerical happens in libgsm_b200.so on the GPU; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+__all__ = [
+    "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "PointSet", "CartesianGrid", "GeoTable",
+    "georef", "IDW", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
+    "predict", "predictprob", "status", "fitpredict", "default_context", "set_default_device",
+]
+
+
+# ---------------------------------------------------------------------------------------------
+# geostatistical functions (the GeoStatsFunctions subset the GPU path claims)
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class _Variogram:
+    sill: float = 1.0
+    range: float = 1.0
+    nugget: float = 0.0
+    kind = -1
+
+    def scaled(self, alpha):
+        return type(self)(sill=self.sill, range=alpha * self.range, nugget=self.nugget)
+
+    def _c(self):
+        return _lib.make_variogram(self.kind, self.sill, self.nugget, self.range)
+
+
+class GaussianVariogram(_Variogram):
+    kind = _lib.GSM_VARIO_GAUSSIAN
+
+
+class SphericalVariogram(_Variogram):
+    kind = _lib.GSM_VARIO_SPHERICAL
+
+
+class ExponentialVariogram(_Variogram):
+    kind = _lib.GSM_VARIO_EXPONENTIAL
+
+
+# ---------------------------------------------------------------------------------------------
+# domains and geotables (the Meshes / GeoTables subset the GPU path claims)
+# ---------------------------------------------------------------------------------------------
+class PointSet:
+    def __init__(self, coords):
+        c = np.asarray(coords, dtype=np.float64)
+        if c.ndim == 1:
+            c = c[:, None]
+        if c.ndim != 2 or not 1 <= c.shape[1] <= 3:
+            raise ValueError("PointSet needs an (n, dim) coordinate array with dim in 1..3")
+        self.coords = np.ascontiguousarray(c)
+
+    @property
+    def dim(self):
+        return self.coords.shape[1]
+
+    def nelements(self):
+        return self.coords.shape[0]
+
+    def __eq__(self, other):
+        return isinstance(other, PointSet) and np.array_equal(self.coords, other.coords)
+
+    def _absmax(self):  # _scalefactor(domain), models.jl:286-291
+        return float(np.abs(self.coords).max())
+
+
+class CartesianGrid:
+    """CartesianGrid(nx, ny[, nz]) -> origin 0, unit spacing;
+    CartesianGrid(lower, upper, dims=(..)) -> spacing (upper-lower)/dims, as in Meshes."""
+
+    def __init__(self, *args, dims=None):
+        if dims is None:
+            self.dims = tuple(int(a) for a in args)
+            self.origin = tuple(0.0 for _ in self.dims)
+            self.spacing = tuple(1.0 for _ in self.dims)
+        else:
+            lo, hi = args
+            self.dims = tuple(int(d) for d in dims)
+            self.origin = tuple(float(x) for x in lo)
+            self.spacing = tuple((float(h) - float(l)) / d for l, h, d in zip(lo, hi, self.dims))
+        if not 1 <= len(self.dims) <= 3:
+            raise ValueError("CartesianGrid supports 1 to 3 dimensions")
+
+    @property
+    def dim(self):
+        return len(self.dims)
+
+    def nelements(self):
+        return int(np.prod(self.dims))
+
+    def __eq__(self, other):
+        return (isinstance(other, CartesianGrid) and self.dims == other.dims and self.origin == other.origin
+                and self.spacing == other.spacing)
+
+    def _absmax(self):  # bounding box corners, models.jl:286-291
+        lo = np.asarray(self.origin)
+        hi = lo + np.asarray(self.dims, dtype=np.float64) * np.asarray(self.spacing)
+        return float(max(np.abs(lo).max(), np.abs(hi).max()))
+
+
+class GeoTable:
+    """georef(table, domain): named columns of values attached to a domain."""
+
+    def __init__(self, table: dict, domain):
+        self.table = {k: v for k, v in table.items()}
+        self.domain = domain
+        for k, v in self.table.items():
+            if len(v) != domain.nelements():
+                raise ValueError(f"column {k!r} does not have one value per element")
+
+    @property
+    def geometry(self):
+        return self.domain
+
+    def __getattr__(self, name):
+        t = self.__dict__.get("table", {})
+        if name in t:
+            return t[name]
+        raise AttributeError(name)
+
+    def names(self):
+        return tuple(self.table.keys())
+
+    def __eq__(self, other):
+        return (isinstance(other, GeoTable) and self.domain == other.domain and self.names() == other.names()
+                and all(_col_equal(self.table[k], other.table[k]) for k in self.table))
+
+
+def _col_equal(a, b):
+    if isinstance(a, Normal) or isinstance(b, Normal):
+        return isinstance(a, Normal) and isinstance(b, Normal) and np.array_equal(a.mu, b.mu) and np.array_equal(a.sigma, b.sigma)
+    return np.array_equal(np.ma.filled(a, np.nan), np.ma.filled(b, np.nan), equal_nan=True)
+
+
+def georef(table: dict, domain) -> GeoTable:
+    if not isinstance(domain, (PointSet, CartesianGrid)):
+        domain = PointSet(domain)
+    return GeoTable(table, domain)
+
+
+@dataclass
+class Normal:
+    """Normal(mu, sigma), scalar or column.  NOTE (reference quirk, copied not fixed): on the
+    ``fitpredict(prob=true)`` path models.jl:298-299 builds ``Normal.(mean, var)``, so ``sigma`` there
+    holds the Kriging VARIANCE (+1e-10); ``predictprob(fitted, :z, p)`` (krig.jl:223-229) holds sqrt."""
+    mu: object
+    sigma: object
+
+    def mean(self):
+        return self.mu
+
+
+# ---------------------------------------------------------------------------------------------
+# models
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class IDW:
+    exponent: float = 1
+    distance: str = "euclidean"
+
+    def _range(self):
+        return math.inf  # Base.range(::GeoStatsModel) = Inf (models.jl:22)
+
+
+class _KrigingModel:
+    fun: _Variogram
+
+    def _range(self):  # krig.jl:12
+        return self.fun.range
+
+
+@dataclass(frozen=True)
+class SimpleKriging(_KrigingModel):
+    fun: _Variogram
+    mean: float
+
+    def _scaled(self, a):
+        return SimpleKriging(self.fun.scaled(a), self.mean)
+
+    def _c(self):
+        return _lib.make_model(_lib.GSM_KRIG_SIMPLE, mean=self.mean)
+
+
+@dataclass(frozen=True)
+class OrdinaryKriging(_KrigingModel):
+    fun: _Variogram
+
+    def _scaled(self, a):
+        return OrdinaryKriging(self.fun.scaled(a))
+
+    def _c(self):
+        return _lib.make_model(_lib.GSM_KRIG_ORDINARY)
+
+
+def monomial_exponents(deg: int, dim: int):
+    """universal.jl:68-77: multiexponents per degree, stably sorted by maximum exponent (descending)."""
+    assert deg >= 0, "degree must be nonnegative"   # universal.jl:56
+    assert dim > 0, "dimension must be positive"     # universal.jl:57
+    cols = []
+    for d in range(deg + 1):
+        cols.extend(e for e in itertools.product(range(d, -1, -1), repeat=dim) if sum(e) == d)
+    order = sorted(range(len(cols)), key=lambda i: -max(cols[i]))
+    return tuple(cols[i] for i in order)
+
+
+class UniversalKriging(_KrigingModel):
+    """UniversalKriging(fun, deg, dim) (universal.jl:50).  Arbitrary drift closures (universal.jl:26)
+    cannot cross a C ABI; pass a table of monomial exponents instead: UniversalKriging(fun, exps=[...])."""
+
+    def __init__(self, fun, deg=None, dim=None, exps=None):
+        self.fun = fun
+        if exps is None:
+            exps = monomial_exponents(int(deg), int(dim))
+        self.exps = tuple(tuple(int(x) for x in e) for e in exps)
+        if not 1 <= len(self.exps) <= _lib.GSM_MAX_DRIFT:
+            raise ValueError("number of drift monomials must be in 1..10")
+
+    def _scaled(self, a):
+        return UniversalKriging(self.fun.scaled(a), exps=self.exps)
+
+    def _c(self):
+        return _lib.make_model(_lib.GSM_KRIG_UNIVERSAL, exps=self.exps)
+
+
+def Kriging(fun, *args):
+    """krig.jl:423-427: Kriging(f) -> OK, Kriging(f, mu) -> SK, Kriging(f, deg, dim) -> UK."""
+    if len(args) == 0:
+        return OrdinaryKriging(fun)
+    if len(args) == 1 and isinstance(args[0], (int, float)) and not isinstance(args[0], bool):
+        return SimpleKriging(fun, float(args[0]))
+    if len(args) == 2:
+        return UniversalKriging(fun, int(args[0]), int(args[1]))
+    if len(args) == 1:
+        return UniversalKriging(fun, exps=args[0])
+    raise TypeError("unsupported Kriging constructor arguments")
+
+
+# ---------------------------------------------------------------------------------------------
+# device context management (one context per GPU per process)
+# ---------------------------------------------------------------------------------------------
+_CTX: dict[int, _lib.Context] = {}
+_DEFAULT_DEVICE = 0
+
+
+def set_default_device(device: int):
+    global _DEFAULT_DEVICE
+    _DEFAULT_DEVICE = int(device)
+
+
+def default_context(device: int | None = None) -> _lib.Context:
+    dev = _DEFAULT_DEVICE if device is None else int(device)
+    if dev not in _CTX:
+        _CTX[dev] = _lib.Context(dev)
+    return _CTX[dev]
+
+
+# ---------------------------------------------------------------------------------------------
+# fit / predict / predictprob / status
+# ---------------------------------------------------------------------------------------------
+def _single_column(data: GeoTable):
+    names = data.names()
+    return names
+
+
+def _checkcompat(model, data: GeoTable):  # krig.jl:78-85
+    nfeat = len(data.names())
+    if isinstance(model, _KrigingModel) and nfeat != 1:
+        raise ValueError(f"{nfeat} data column(s) provided to 1-variate Kriging model")
+
+
+def _pointset_of(domain) -> np.ndarray:
+    """_pointsupport (models.jl:265-270): centroids of the data domain."""
+    if isinstance(domain, PointSet):
+        return domain.coords
+    raise NotImplementedError("GPU path claims PointSet data only")
+
+
+class FittedKriging:
+    def __init__(self, model, data, ctx, gfit, alpha=1.0):
+        self.model, self.data, self._ctx, self._gfit, self._alpha = model, data, ctx, gfit, alpha
+
+
+class FittedIDW:
+    def __init__(self, model, data, ctx, alpha=1.0):
+        self.model, self.data, self._ctx, self._alpha = model, data, ctx, alpha
+
+
+def fit(model, data: GeoTable, *, device=None, _alpha=1.0):
+    """fit(model, geotable) (models.jl:38; krig.jl:58-75; idw.jl:43-49)."""
+    _checkcompat(model, data)
+    ctx = _lib.Context(_DEFAULT_DEVICE if device is None else device)  # a fitted model owns its samples
+    X = _pointset_of(data.domain) * _alpha if _alpha != 1.0 else _pointset_of(data.domain)
+    var = data.names()[0]
+    ctx.set_samples(X, np.asarray(data.table[var], dtype=np.float64))
+    if isinstance(model, IDW):
+        return FittedIDW(model, data, ctx, _alpha)
+    m = model._scaled(_alpha) if _alpha != 1.0 else model
+    gfit = ctx.global_fit(m.fun._c(), m._c())
+    return FittedKriging(model, data, ctx, gfit, _alpha)
+
+
+def status(fitted) -> bool:
+    """status(fitted) (krig.jl:49-52; idw.jl:36)."""
+    if isinstance(fitted, FittedIDW):
+        return True
+    return fitted._gfit.status()
+
+
+def _as_point(g, dim):
+    p = np.asarray(g.coords if isinstance(g, PointSet) else g, dtype=np.float64).reshape(1, -1)
+    if p.shape[1] != dim:
+        raise ValueError("point has the wrong dimension")
+    return p
+
+
+def _check_vars(fitted, var):
+    """Returns (name, scalar?) and mirrors the ArgumentError of models.jl:56-57 / 71-72."""
+    if isinstance(var, str):
+        names = (var,)
+        scalar = True
+    else:
+        names = tuple(var)
+        scalar = False
+        if len(names) > 1:
+            raise ValueError("cannot use univariate model to predict multiple variables")
+    if names[0] not in fitted.data.names():
+        raise KeyError(names[0])
+    return names[0], scalar
+
+
+def predict(fitted, var, g):
+    """predict(fitted, var, g) (krig.jl:215-219; idw.jl:55)."""
+    _, scalar = _check_vars(fitted, var)
+    p = _as_point(g, fitted._ctx.dim) * fitted._alpha
+    t = _lib.Context.point_targets(p)
+    if isinstance(fitted, FittedIDW):
+        mean, _ = fitted._ctx.idw(fitted.model.exponent, t)
+    else:
+        mean, _ = fitted._gfit.predict(t, want_var=False)
+    return float(mean[0]) if scalar else [float(mean[0])]
+
+
+def predictprob(fitted, var, g):
+    """predictprob(fitted, var, g): Normal(mu, sqrt(var)) for Kriging (krig.jl:223-229)."""
+    _, scalar = _check_vars(fitted, var)
+    p = _as_point(g, fitted._ctx.dim) * fitted._alpha
+    t = _lib.Context.point_targets(p)
+    if isinstance(fitted, FittedIDW):
+        raise NotImplementedError("IDW predictprob (Dirac) is not claimed by the GPU path")
+    mean, var_ = fitted._gfit.predict(t, want_var=True)
+    if var_[0] < 0:
+        raise ValueError("DomainError: sqrt of negative variance")  # krig.jl:228
+    d = Normal(float(mean[0]), math.sqrt(float(var_[0])))
+    return d if scalar else [d]
+
+
+# ---------------------------------------------------------------------------------------------
+# fitpredict
+# ---------------------------------------------------------------------------------------------
+def _scale_factor(model, data_dom, dom) -> float:
+    """alpha of `_scale` (models.jl:272-284)."""
+    r = model._range()
+    a1 = 1.0 if math.isinf(r) else r
+    return 1.0 / max(a1, data_dom._absmax(), dom._absmax())
+
+
+def _targets_for(dom, alpha, first=0, count=-1):
+    if isinstance(dom, CartesianGrid):
+        origin = tuple(alpha * np.float64(o) for o in dom.origin)
+        spacing = tuple(alpha * np.float64(s) for s in dom.spacing)
+        return _lib.Context.grid_targets(origin, spacing, dom.dims, first, count)
+    return _lib.Context.point_targets(dom.coords * alpha, first=first, count=count)
+
+
+def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=True, minneighbors=1,
+               maxneighbors=10, neighborhood=None, distance="euclidean", device=None, first=0, count=-1,
+               ctx=None):
+    """fitpredict(model, geotable, domain; options) (models.jl:102-129).
+
+    ``first``/``count`` (not in the reference) select a contiguous shard of the target index for
+    multi-GPU runs: every rank predicts its slab of the same domain (models.jl:236-247 chunking)."""
+    if not point:
+        raise NotImplementedError("change of support (point=false) is not claimed by the GPU path")
+    if distance != "euclidean":
+        raise NotImplementedError("only the Euclidean distance is claimed by the GPU path")
+    if not isinstance(dom, (PointSet, CartesianGrid)):
+        dom = PointSet(dom)
+    _checkcompat(model, data)
+    names = data.names()
+    if len(names) != 1:
+        raise NotImplementedError("GPU path claims univariate tables only")
+    z = np.asarray(data.table[names[0]], dtype=np.float64)
+    if np.isnan(z).any():
+        raise NotImplementedError("missing values are not claimed by the GPU path")
+    X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
+    alpha = _scale_factor(model, data.domain, dom)     # _scale, models.jl:118
+    ctx = ctx or default_context(device)
+    ctx.set_samples(X * alpha, z)
+    t = _targets_for(dom, alpha, first, count)
+    radius = 0.0
+    if neighborhood is not None:
+        radius = alpha * float(neighborhood)           # sneigh = alpha * neigh (models.jl:281), ball radius
+    M = _lib.Context.target_count(t)
+    if isinstance(model, IDW):
+        if prob:
+            raise NotImplementedError("IDW with prob=true is not claimed by the GPU path")
+        if neighbors:
+            mean, st = ctx.idw(model.exponent, t, maxneighbors=_clamp_max(maxneighbors, len(z)),
+                               minneighbors=minneighbors, radius=radius)
+        else:
+            mean, st = ctx.idw(model.exponent, t)
+        col = _mask_missing(mean, st)
+    else:
+        sm = model._scaled(alpha)
+        if neighbors:
+            mean, var, st, _ = ctx.local_krige(sm.fun._c(), sm._c(), t, _clamp_max(maxneighbors, len(z)),
+                                               minneighbors, radius, want_var=prob)
+        else:
+            gfit = ctx.global_fit(sm.fun._c(), sm._c())
+            mean, var = gfit.predict(t, want_var=prob)
+            st = np.zeros(M, dtype=np.uint8)
+            gfit.close()
+        if prob:
+            if np.any(var[st == 0] <= 0):
+                raise ValueError("PosDefException: non-positive Kriging variance")  # MvNormal(mu, Sigma), krig.jl:236
+            col = Normal(_mask_missing(mean, st), _mask_missing(var, st))  # Normal.(mean, var), models.jl:298-299
+        else:
+            col = _mask_missing(mean, st)
+    out_dom = dom if (first == 0 and count < 0) else None
+    pred = GeoTable.__new__(GeoTable)
+    pred.table = {names[0]: col}
+    pred.domain = out_dom if out_dom is not None else dom   # georef over the ORIGINAL domain, models.jl:128
+    pred.shard = (first, M)
+    return pred
+
+
+def _clamp_max(maxneighbors, nobs):
+    return nobs if (maxneighbors > nobs or maxneighbors < 1) else maxneighbors   # models.jl:144-147
+
+
+def _mask_missing(a, st):
+    miss = st == _lib.GSM_ST_MISSING
+    if miss.any():
+        return np.ma.masked_array(a, mask=miss)   # `missing` predictions, models.jl:178-181
+    return a

@@ -1,0 +1,517 @@
+// C-ABI glue of libgsm_b200.so (declarations and reference citations: include/gsm_b200.h).
+// Owns the context, moves data, chunks the target range and sequences the kernels; no arithmetic of
+// the hot path lives here.  Never throws; every failure is an int code + gsm_last_error message.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "gsm_internal.cuh"
+
+static thread_local std::string g_create_error;
+
+void gsm_set_error(gsm_ctx* ctx, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  else g_create_error = msg;
+}
+
+bool gsm_is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int gsm_reserve(gsm_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return GSM_OK;
+  if (b.p) GSM_CUDA(ctx, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = std::max<size_t>(bytes, 256);
+  GSM_CUDA(ctx, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return GSM_OK;
+}
+
+static void free_buf(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+VarioDev make_vario(const gsm_variogram& v) {
+  VarioDev d;
+  d.kind = v.kind;
+  d.sill = v.sill;
+  d.nugget = v.nugget;
+  d.range = v.range;
+  d.inv_range = 1.0 / v.range;
+  d.cs = v.sill - v.nugget;
+  d.nadd = v.kind == GSM_VARIO_GAUSSIAN ? v.nugget + 1e-6 : v.nugget;
+  return d;
+}
+
+int check_vario(gsm_ctx* ctx, const gsm_variogram* v) {
+  if (!v || v->kind < GSM_VARIO_GAUSSIAN || v->kind > GSM_VARIO_EXPONENTIAL || !(v->range > 0.0) ||
+      !std::isfinite(v->range) || !std::isfinite(v->sill) || !std::isfinite(v->nugget)) {
+    gsm_set_error(ctx, "invalid variogram descriptor");
+    return GSM_ERR_INVALID;
+  }
+  return GSM_OK;
+}
+
+int make_model(gsm_ctx* ctx, const gsm_model* m, int dim, ModelDev& d) {
+  if (!m || m->kind < GSM_KRIG_SIMPLE || m->kind > GSM_KRIG_UNIVERSAL) {
+    gsm_set_error(ctx, "invalid Kriging model descriptor");
+    return GSM_ERR_INVALID;
+  }
+  d.kind = m->kind;
+  d.mean = m->mean;
+  d.ndrift = 0;
+  memset(d.exps, 0, sizeof(d.exps));
+  if (m->kind == GSM_KRIG_UNIVERSAL) {
+    if (m->ndrift < 1 || m->ndrift > GSM_MAX_DRIFT) {
+      gsm_set_error(ctx, "UniversalKriging: ndrift must be in 1..GSM_MAX_DRIFT");
+      return GSM_ERR_INVALID;
+    }
+    d.ndrift = m->ndrift;
+    for (int n = 0; n < m->ndrift; ++n)
+      for (int c = 0; c < 3; ++c) {
+        int e = m->exps[n][c];
+        if (e < 0 || (c >= dim && e != 0)) {  // universal.jl:56-57 degree must be nonnegative
+          gsm_set_error(ctx, "UniversalKriging: invalid monomial exponent");
+          return GSM_ERR_INVALID;
+        }
+        d.exps[n][c] = e;
+      }
+  }
+  return GSM_OK;
+}
+
+long long domain_size(const gsm_targets* t) {
+  if (t->kind == GSM_TARGETS_GRID) {
+    long long m = 1;
+    for (int d = 0; d < t->dim; ++d) m *= t->dims[d];
+    return m;
+  }
+  return t->npoints;
+}
+
+// Resolve the descriptor into a device-side view of the shard [first, first+count).
+int make_targets(gsm_ctx* ctx, const gsm_targets* t, TargetsDev& d, long long& M) {
+  if (!t || (t->kind != GSM_TARGETS_GRID && t->kind != GSM_TARGETS_POINTS) || t->dim < 1 || t->dim > 3) {
+    gsm_set_error(ctx, "invalid target domain descriptor");
+    return GSM_ERR_INVALID;
+  }
+  if (t->dim != ctx->dim) {
+    gsm_set_error(ctx, "target domain and samples have different dimensions");
+    return GSM_ERR_INVALID;
+  }
+  const long long total = domain_size(t);
+  long long first = t->first, count = t->count < 0 ? total - t->first : t->count;
+  if (first < 0 || count < 0 || first + count > total) {
+    gsm_set_error(ctx, "target shard [first, first+count) is outside the domain");
+    return GSM_ERR_INVALID;
+  }
+  M = count;
+  d.kind = t->kind;
+  d.dim = t->dim;
+  d.points = nullptr;
+  for (int c = 0; c < 3; ++c) {
+    d.origin[c] = c < t->dim ? t->origin[c] : 0.0;
+    d.spacing[c] = c < t->dim ? t->spacing[c] : 0.0;
+    d.dims[c] = c < t->dim ? t->dims[c] : 1;
+  }
+  d.first = first;
+  d.count = count;
+  if (t->kind == GSM_TARGETS_GRID) {
+    for (int c = 0; c < t->dim; ++c)
+      if (t->dims[c] < 1) {
+        gsm_set_error(ctx, "grid dims must be positive");
+        return GSM_ERR_INVALID;
+      }
+  } else {
+    if (!t->points && count > 0) {
+      gsm_set_error(ctx, "PointSet targets need a coordinate pointer");
+      return GSM_ERR_INVALID;
+    }
+    const double* src = t->points + first * t->dim;
+    if (gsm_is_device_ptr(t->points)) {
+      d.points = src;
+    } else {
+      GSM_CHECK(gsm_reserve(ctx, ctx->tgt_points, (size_t)count * t->dim * sizeof(double)));
+      GSM_CUDA(ctx, cudaMemcpyAsync(ctx->tgt_points.p, src, (size_t)count * t->dim * sizeof(double),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+      d.points = (const double*)ctx->tgt_points.p;
+    }
+    d.first = 0;  // points view already starts at the shard
+  }
+  return GSM_OK;
+}
+
+void clamp_neighbors(long long nobs, const gsm_neighbor_opts* o, int& maxn, int& minn) {
+  long long mx = o->maxneighbors, mn = o->minneighbors;
+  if (mx > nobs || mx < 1) mx = nobs;   // models.jl:144-147
+  if (mn > mx || mn < 1) mn = 1;        // models.jl:148-150
+  maxn = (int)std::min<long long>(mx, 1 << 30);
+  minn = (int)mn;
+}
+
+// An output the caller may hand us as host or device memory.
+template <typename T>
+struct OutBuf {
+  T* user = nullptr;
+  T* dev = nullptr;   // where kernels write
+  bool staged = false;
+  int init(gsm_ctx* ctx, T* user_ptr, DevBuf& stage, long long M) {
+    user = user_ptr;
+    if (!user_ptr) {
+      dev = nullptr;
+      return GSM_OK;
+    }
+    if (gsm_is_device_ptr(user_ptr)) {
+      dev = user_ptr;
+      staged = false;
+    } else {
+      GSM_CHECK(gsm_reserve(ctx, stage, (size_t)std::max<long long>(M, 1) * sizeof(T)));
+      dev = (T*)stage.p;
+      staged = true;
+    }
+    return GSM_OK;
+  }
+  int download(gsm_ctx* ctx, long long off, long long cnt, cudaStream_t st) {
+    if (!staged || cnt <= 0) return GSM_OK;
+    GSM_CUDA(ctx, cudaMemcpyAsync(user + off, dev + off, (size_t)cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return GSM_OK;
+  }
+};
+
+constexpr long long CHUNK = 1LL << 20;  // targets per kernel wave (bounds the neighbour scratch)
+
+struct EventTimer {
+  std::vector<cudaEvent_t> evs;
+  cudaEvent_t mark(cudaStream_t st) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    evs.push_back(e);
+    return e;
+  }
+  static double ms(cudaEvent_t a, cudaEvent_t b) {
+    float f = 0.f;
+    cudaEventElapsedTime(&f, a, b);
+    return f;
+  }
+  ~EventTimer() {
+    for (auto e : evs) cudaEventDestroy(e);
+  }
+};
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int gsm_abi_version(void) { return GSM_ABI_VERSION; }
+
+int gsm_create(int device, gsm_ctx** out) {
+  if (!out) return GSM_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    gsm_set_error(nullptr, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                               " (libgsm_b200 has no CPU fallback)");
+    return GSM_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) {
+    gsm_set_error(nullptr, "device ordinal out of range");
+    return GSM_ERR_INVALID;
+  }
+  gsm_ctx* ctx = new gsm_ctx();
+  ctx->device = device;
+  DeviceGuard g(device);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    gsm_set_error(nullptr, std::string("stream creation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return GSM_ERR_CUDA;
+  }
+  *out = ctx;
+  return GSM_OK;
+}
+
+int gsm_destroy(gsm_ctx* ctx) {
+  if (!ctx) return GSM_OK;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  DevBuf* bufs[] = {&ctx->coords, &ctx->values, &ctx->rec, &ctx->sidx, &ctx->cell_of, &ctx->cell_start,
+                    &ctx->cell_fill, &ctx->cub_tmp, &ctx->red, &ctx->nbr_pos, &ctx->nbr_cnt, &ctx->out_mean,
+                    &ctx->out_var, &ctx->out_status, &ctx->out_nbr, &ctx->tgt_points};
+  for (DevBuf* b : bufs) free_buf(*b);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return GSM_OK;
+}
+
+const char* gsm_last_error(const gsm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gsm_get_timings(const gsm_ctx* ctx, gsm_timings* out) {
+  if (!ctx || !out) return GSM_ERR_INVALID;
+  *out = ctx->tim;
+  return GSM_OK;
+}
+
+int gsm_synchronize(gsm_ctx* ctx) {
+  if (!ctx) return GSM_ERR_INVALID;
+  DeviceGuard g(ctx->device);
+  GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  GSM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return GSM_OK;
+}
+
+int gsm_host_alloc(void** out, int64_t bytes) {
+  if (!out || bytes < 0) return GSM_ERR_INVALID;
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    gsm_set_error(nullptr, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return GSM_ERR_CUDA;
+  }
+  return GSM_OK;
+}
+
+int gsm_host_free(void* p) {
+  if (!p) return GSM_OK;
+  return cudaFreeHost(p) == cudaSuccess ? GSM_OK : GSM_ERR_CUDA;
+}
+
+int gsm_set_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values) {
+  if (!ctx) return GSM_ERR_INVALID;
+  if (!coords || !values || dim < 1 || dim > 3 || n < 1) {
+    gsm_set_error(ctx, "gsm_set_samples: need coords, values, 1 <= dim <= 3 and n >= 1");
+    return GSM_ERR_INVALID;
+  }
+  DeviceGuard g(ctx->device);
+  ctx->tim = gsm_timings{};
+  EventTimer et;
+  cudaEvent_t e0 = et.mark(ctx->stream);
+  GSM_CHECK(gsm_reserve(ctx, ctx->coords, (size_t)n * dim * sizeof(double)));
+  GSM_CHECK(gsm_reserve(ctx, ctx->values, (size_t)n * sizeof(double)));
+  GSM_CUDA(ctx, cudaMemcpyAsync(ctx->coords.p, coords, (size_t)n * dim * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GSM_CUDA(ctx, cudaMemcpyAsync(ctx->values.p, values, (size_t)n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  cudaEvent_t e1 = et.mark(ctx->stream);
+  ctx->dim = dim;
+  ctx->n = n;
+  int rc = gsm_build_bins(ctx);
+  if (rc != GSM_OK) {
+    ctx->n = 0;
+    return rc;
+  }
+  cudaEvent_t e2 = et.mark(ctx->stream);
+  GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->tim.h2d_ms = EventTimer::ms(e0, e1);
+  ctx->tim.bin_ms = EventTimer::ms(e1, e2);
+  ctx->tim.total_ms = EventTimer::ms(e0, e2);
+  return GSM_OK;
+}
+
+// Shared driver of the neighbourhood-based entry points.
+//   mode 0: kNN only, 1: local Kriging, 2: local IDW
+static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const gsm_model* model, double exponent,
+                     const gsm_targets* targets, const gsm_neighbor_opts* opts, double* out_mean, double* out_var,
+                     uint8_t* out_status, int32_t* out_nbr, int32_t* out_n) {
+  if (!ctx) return GSM_ERR_INVALID;
+  if (ctx->n <= 0) {
+    gsm_set_error(ctx, "no samples: call gsm_set_samples first");
+    return GSM_ERR_NO_SAMPLES;
+  }
+  if (!opts) {
+    gsm_set_error(ctx, "neighbour options are required");
+    return GSM_ERR_INVALID;
+  }
+  DeviceGuard g(ctx->device);
+  ctx->tim = gsm_timings{};
+  VarioDev vd{};
+  ModelDev md{};
+  if (mode == 1) {
+    GSM_CHECK(check_vario(ctx, vario));
+    vd = make_vario(*vario);
+    GSM_CHECK(make_model(ctx, model, ctx->dim, md));
+    if (!out_mean) {
+      gsm_set_error(ctx, "out_mean is required");
+      return GSM_ERR_INVALID;
+    }
+  }
+  int maxn, minn;
+  clamp_neighbors(ctx->n, opts, maxn, minn);
+  if (maxn > GSM_MAX_NEIGHBORS) {
+    gsm_set_error(ctx, "maxneighbors (after clamping to the number of samples) exceeds GSM_MAX_NEIGHBORS");
+    return GSM_ERR_UNSUPPORTED;
+  }
+  if (mode == 1 && maxn > 32) {
+    gsm_set_error(ctx, "local Kriging supports at most 32 neighbours in this build");
+    return GSM_ERR_UNSUPPORTED;
+  }
+  EventTimer et;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t e_begin = et.mark(st);
+  TargetsDev td{};
+  long long M = 0;
+  GSM_CHECK(make_targets(ctx, targets, td, M));
+  cudaEvent_t e_h2d = et.mark(st);
+
+  OutBuf<double> omean, ovar;
+  OutBuf<uint8_t> ostat;
+  OutBuf<int32_t> onbr, on;
+  GSM_CHECK(omean.init(ctx, out_mean, ctx->out_mean, M));
+  GSM_CHECK(ovar.init(ctx, out_var, ctx->out_var, M));
+  GSM_CHECK(ostat.init(ctx, out_status, ctx->out_status, M));
+  GSM_CHECK(onbr.init(ctx, out_nbr, ctx->out_nbr, M * maxn));
+  const long long chunk = std::min<long long>(CHUNK, std::max<long long>(M, 1));
+  GSM_CHECK(gsm_reserve(ctx, ctx->nbr_pos, (size_t)chunk * maxn * sizeof(int)));
+  DevBuf& cntbuf = ctx->nbr_cnt;
+  GSM_CHECK(gsm_reserve(ctx, cntbuf, (size_t)std::max<long long>(M, 1) * sizeof(int)));
+  int* d_cnt_all = (int*)cntbuf.p;
+  if (out_n && gsm_is_device_ptr(out_n)) d_cnt_all = out_n;
+
+  double knn_ms = 0, solve_ms = 0;
+  std::vector<cudaEvent_t> marks;
+  std::vector<cudaEvent_t> chunk_done;
+  for (long long off = 0; off < M; off += chunk) {
+    TargetsDev tc = td;
+    tc.first = td.first + off;
+    tc.count = std::min(chunk, M - off);
+    if (td.kind == GSM_TARGETS_POINTS) {
+      tc.first = 0;
+      tc.points = td.points + off * td.dim;
+    }
+    int* d_pos = (int*)ctx->nbr_pos.p;
+    int* d_cnt = d_cnt_all + off;
+    cudaEvent_t a = et.mark(st);
+    GSM_CHECK(gsm_launch_knn(ctx, tc, maxn, opts->radius, d_pos, d_cnt));
+    cudaEvent_t bq = et.mark(st);
+    if (onbr.dev) GSM_CHECK(gsm_launch_nbr_to_rows(ctx, d_pos, tc.count * maxn, onbr.dev + off * maxn));
+    if (mode == 1) {
+      GSM_CHECK(gsm_launch_local_krige(ctx, vd, md, tc, maxn, minn, d_pos, d_cnt, omean.dev + off,
+                                       ovar.dev ? ovar.dev + off : nullptr, ostat.dev ? ostat.dev + off : nullptr));
+    } else if (mode == 2) {
+      GSM_CHECK(gsm_launch_idw_local(ctx, exponent, tc, maxn, minn, d_pos, d_cnt, omean.dev + off,
+                                     ostat.dev ? ostat.dev + off : nullptr));
+    }
+    cudaEvent_t c = et.mark(st);
+    marks.push_back(a);
+    marks.push_back(bq);
+    marks.push_back(c);
+    // overlap this chunk's download with the next chunk's kernels
+    GSM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, c, 0));
+    GSM_CHECK(omean.download(ctx, off, tc.count, ctx->copy_stream));
+    GSM_CHECK(ovar.download(ctx, off, tc.count, ctx->copy_stream));
+    GSM_CHECK(ostat.download(ctx, off, tc.count, ctx->copy_stream));
+    GSM_CHECK(onbr.download(ctx, off * maxn, tc.count * maxn, ctx->copy_stream));
+    if (out_n && d_cnt_all != out_n)
+      GSM_CUDA(ctx, cudaMemcpyAsync(out_n + off, d_cnt, (size_t)tc.count * sizeof(int), cudaMemcpyDeviceToHost,
+                                    ctx->copy_stream));
+  }
+  cudaEvent_t e_k = et.mark(st);
+  cudaEvent_t e_copy = et.mark(ctx->copy_stream);
+  GSM_CUDA(ctx, cudaStreamSynchronize(st));
+  GSM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  for (size_t i = 0; i + 3 <= marks.size(); i += 3) {
+    knn_ms += EventTimer::ms(marks[i], marks[i + 1]);
+    solve_ms += EventTimer::ms(marks[i + 1], marks[i + 2]);
+  }
+  ctx->tim.h2d_ms = EventTimer::ms(e_begin, e_h2d);
+  ctx->tim.knn_ms = knn_ms;
+  ctx->tim.solve_ms = solve_ms;
+  ctx->tim.bin_ms = 0;
+  double t_k = EventTimer::ms(e_begin, e_k);
+  double t_c = EventTimer::ms(e_begin, e_copy);
+  ctx->tim.total_ms = std::max(t_k, t_c);
+  ctx->tim.d2h_ms = std::max(0.0, t_c - t_k);  // download time NOT hidden behind kernels
+  return GSM_OK;
+}
+
+int gsm_knn(gsm_ctx* ctx, const gsm_targets* targets, const gsm_neighbor_opts* opts, int32_t* out_idx,
+            int32_t* out_n) {
+  return run_local(ctx, 0, nullptr, nullptr, 0.0, targets, opts, nullptr, nullptr, nullptr, out_idx, out_n);
+}
+
+int gsm_local_krige(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_model* model, const gsm_targets* targets,
+                    const gsm_neighbor_opts* opts, double* out_mean, double* out_var, uint8_t* out_status,
+                    int32_t* out_nbr) {
+  return run_local(ctx, 1, vario, model, 0.0, targets, opts, out_mean, out_var, out_status, out_nbr, nullptr);
+}
+
+int gsm_idw(gsm_ctx* ctx, double exponent, const gsm_targets* targets, const gsm_neighbor_opts* opts,
+            double* out_mean, uint8_t* out_status) {
+  if (!ctx) return GSM_ERR_INVALID;
+  if (!out_mean) {
+    gsm_set_error(ctx, "out_mean is required");
+    return GSM_ERR_INVALID;
+  }
+  if (!(exponent > 0.0) || !std::isfinite(exponent)) {
+    gsm_set_error(ctx, "IDW exponent must be positive and finite");
+    return GSM_ERR_INVALID;
+  }
+  if (opts && opts->maxneighbors != 0)
+    return run_local(ctx, 2, nullptr, nullptr, exponent, targets, opts, out_mean, nullptr, out_status, nullptr, nullptr);
+  if (ctx->n <= 0) {
+    gsm_set_error(ctx, "no samples: call gsm_set_samples first");
+    return GSM_ERR_NO_SAMPLES;
+  }
+  DeviceGuard g(ctx->device);
+  ctx->tim = gsm_timings{};
+  EventTimer et;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t e0 = et.mark(st);
+  TargetsDev td{};
+  long long M = 0;
+  GSM_CHECK(make_targets(ctx, targets, td, M));
+  cudaEvent_t e1 = et.mark(st);
+  OutBuf<double> omean;
+  OutBuf<uint8_t> ostat;
+  GSM_CHECK(omean.init(ctx, out_mean, ctx->out_mean, M));
+  GSM_CHECK(ostat.init(ctx, out_status, ctx->out_status, M));
+  GSM_CHECK(gsm_launch_idw_global(ctx, exponent, td, omean.dev));
+  if (ostat.dev) GSM_CUDA(ctx, cudaMemsetAsync(ostat.dev, 0, (size_t)M, st));
+  cudaEvent_t e2 = et.mark(st);
+  GSM_CHECK(omean.download(ctx, 0, M, st));
+  GSM_CHECK(ostat.download(ctx, 0, M, st));
+  cudaEvent_t e3 = et.mark(st);
+  GSM_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->tim.h2d_ms = EventTimer::ms(e0, e1);
+  ctx->tim.solve_ms = EventTimer::ms(e1, e2);
+  ctx->tim.d2h_ms = EventTimer::ms(e2, e3);
+  ctx->tim.total_ms = EventTimer::ms(e0, e3);
+  return GSM_OK;
+}
+
+int gsm_measure_fp64_peak(gsm_ctx* ctx, double* out_dfma_tflops, double* out_dmma_tflops) {
+  if (!ctx) return GSM_ERR_INVALID;
+  DeviceGuard g(ctx->device);
+  return gsm_fp64_peak(ctx, out_dfma_tflops, out_dmma_tflops);
+}
+
+}  // extern "C"

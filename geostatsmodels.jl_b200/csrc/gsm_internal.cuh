@@ -1,0 +1,208 @@
+// Internal declarations shared by the kernels and the C-ABI glue of libgsm_b200.so.
+// Nothing here is part of the public ABI (see include/gsm_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "gsm_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every CUDA call funnels through GSM_CUDA so failures surface as GSM_ERR_CUDA
+// with a message retrievable through gsm_last_error (the C layer never throws).
+// ---------------------------------------------------------------------------------------------
+#define GSM_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      gsm_set_error((ctx), std::string(#call) + ": " + cudaGetErrorString(e_) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));               \
+      return GSM_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define GSM_CHECK(expr)        \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != GSM_OK) return rc_; \
+  } while (0)
+
+void gsm_set_error(gsm_ctx* ctx, const std::string& msg);
+
+// ---------------------------------------------------------------------------------------------
+// device-side POD parameter blocks (passed by value as kernel arguments)
+// ---------------------------------------------------------------------------------------------
+struct VarioDev {
+  int kind;
+  double sill, nugget, range, inv_range;
+  double cs;    // sill - nugget (partial sill)
+  double nadd;  // nugget added for h > 0 (Gaussian: nugget + 1e-6)
+};
+
+struct TargetsDev {
+  int kind;               // GSM_TARGETS_GRID / POINTS
+  int dim;                // user dimension (1..3)
+  double origin[3], spacing[3];
+  long long dims[3];
+  const double* points;   // device pointer, npoints x dim (AoS)
+  long long first;        // first linear target index of this launch
+  long long count;        // targets in this launch
+};
+
+struct ModelDev {
+  int kind;
+  int ndrift;
+  double mean;
+  int exps[GSM_MAX_DRIFT][3];
+};
+
+// Uniform grid bins over the sample bounding box (the KNearestSearch index).
+struct BinsDev {
+  double bbmin[3];
+  double h;        // cell edge
+  double inv_h;
+  int nc[3];       // cells per dimension (1 in unused dimensions)
+  const int* cell_start;      // ncells + 1, exclusive prefix of cell counts
+  const double4* rec;         // samples sorted by cell: {x, y, z (0 if dim<3), value}
+  const int* sidx;            // original (0-based) sample row of each sorted record
+  int n;                      // number of samples
+};
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct gsm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_stream = nullptr;  // D2H overlap
+  std::string err;
+  gsm_timings tim{};
+
+  // samples
+  int dim = 0;
+  long long n = 0;
+  DevBuf coords;      // n x dim doubles, caller order (AoS)
+  DevBuf values;      // n doubles
+  DevBuf rec;         // n double4, cell-sorted
+  DevBuf sidx;        // n int, cell-sorted -> original row
+  DevBuf cell_of;     // n int scratch
+  DevBuf cell_start;  // ncells + 1 int
+  DevBuf cell_fill;   // ncells int scratch
+  DevBuf cub_tmp;
+  DevBuf red;         // small reduction scratch
+  BinsDev bins{};
+  double sample_mean = 0.0;
+
+  // per-call scratch
+  DevBuf nbr_pos;     // chunk x k int : positions into rec
+  DevBuf nbr_cnt;     // chunk int
+  DevBuf out_mean, out_var, out_status, out_nbr, tgt_points;
+
+  // events for gsm_timings
+  cudaEvent_t ev[8] = {};
+};
+
+struct gsm_fit {
+  gsm_ctx* ctx = nullptr;
+  gsm_variogram vario{};
+  gsm_model model{};
+  int status = 0;
+  long long n = 0;   // samples
+  int ncon = 0;
+  DevBuf Linv;       // n x n lower-triangular inverse Cholesky factor (column-major)
+  DevBuf W;          // n x (1 + ncon) = Linv * [z, F]
+  DevBuf schur;      // small host-side quantities mirrored to device
+  std::vector<double> S;   // ncon x ncon Cholesky factor of the Schur complement (host)
+  std::vector<double> h;   // ncon: V^T w  (host)
+};
+
+int gsm_reserve(gsm_ctx* ctx, DevBuf& b, size_t bytes);
+bool gsm_is_device_ptr(const void* p);
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (each returns GSM_OK / GSM_ERR_*; all enqueue on ctx->stream)
+// ---------------------------------------------------------------------------------------------
+int gsm_build_bins(gsm_ctx* ctx);
+int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt);
+int gsm_launch_nbr_to_rows(gsm_ctx* ctx, const int* d_pos, long long total, int* d_rows);
+int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k,
+                           int minneighbors, const int* d_pos, const int* d_cnt, double* d_mean,
+                           double* d_var, unsigned char* d_status);
+int gsm_launch_idw_global(gsm_ctx* ctx, double exponent, const TargetsDev& tg, double* d_mean);
+int gsm_launch_idw_local(gsm_ctx* ctx, double exponent, const TargetsDev& tg, int k, int minneighbors,
+                         const int* d_pos, const int* d_cnt, double* d_mean, unsigned char* d_status);
+int gsm_fp64_peak(gsm_ctx* ctx, double* dfma, double* dmma);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Target coordinates of linear index `lin` (0-based over the WHOLE domain).  Grid: centroid
+// (origin + i*spacing) + spacing/2 with every operation rounded once (no FMA) -- the declared
+// arithmetic of include/gsm_b200.h and oracle Grid.centroids.
+__device__ __forceinline__ void gsm_target_coords(const TargetsDev& tg, long long lin, double& x, double& y,
+                                                  double& z) {
+  if (tg.kind == GSM_TARGETS_GRID) {
+    long long i0 = lin % tg.dims[0];
+    long long r = lin / tg.dims[0];
+    long long i1 = r % tg.dims[1];
+    long long i2 = r / tg.dims[1];
+    x = __dadd_rn(__dadd_rn(tg.origin[0], __dmul_rn((double)i0, tg.spacing[0])), __dmul_rn(tg.spacing[0], 0.5));
+    y = __dadd_rn(__dadd_rn(tg.origin[1], __dmul_rn((double)i1, tg.spacing[1])), __dmul_rn(tg.spacing[1], 0.5));
+    z = __dadd_rn(__dadd_rn(tg.origin[2], __dmul_rn((double)i2, tg.spacing[2])), __dmul_rn(tg.spacing[2], 0.5));
+  } else {
+    const double* p = tg.points + lin * tg.dim;
+    x = p[0];
+    y = tg.dim > 1 ? p[1] : 0.0;
+    z = tg.dim > 2 ? p[2] : 0.0;
+  }
+}
+
+// Squared distance key of the neighbour search: ((dx*dx + dy*dy) + dz*dz), each op rounded once.
+// Bit-identical to oracle sqdist_keys (a zero dz term adds exactly 0).
+__device__ __forceinline__ double gsm_d2_key(double ax, double ay, double az, double bx, double by, double bz) {
+  double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Covariance form sill - gamma(h) from a squared distance (krig.jl:165-179 on top of the variogram).
+__device__ __forceinline__ double gsm_cov_d2(const VarioDev& v, double d2) {
+  if (!(d2 > 0.0)) return v.sill;  // gamma(0) = 0
+  double h = sqrt(d2);
+  double t = h * v.inv_range;
+  double g;
+  if (v.kind == GSM_VARIO_SPHERICAL) {
+    g = (h < v.range) ? v.cs * (1.5 * t - 0.5 * (t * t * t)) : v.cs;
+  } else if (v.kind == GSM_VARIO_GAUSSIAN) {
+    g = v.cs * (1.0 - exp(-3.0 * (t * t)));
+  } else {
+    g = v.cs * (1.0 - exp(-3.0 * t));
+  }
+  return v.sill - (g + v.nadd);
+}
+
+__device__ __forceinline__ double gsm_ipow(double x, int p) {
+  double r = 1.0;
+  for (int i = 0; i < p; ++i) r *= x;
+  return r;
+}
+
+__device__ __forceinline__ double gsm_drift(const ModelDev& m, int n, double x, double y, double z) {
+  return gsm_ipow(x, m.exps[n][0]) * gsm_ipow(y, m.exps[n][1]) * gsm_ipow(z, m.exps[n][2]);
+}
+
+__device__ __forceinline__ double gsm_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double gsm_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double gsm_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += gsm_shfl_xor(v, o);
+  return v;
+}
+#endif

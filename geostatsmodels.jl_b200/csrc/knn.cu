@@ -1,0 +1,217 @@
+// Exact k-nearest-neighbour search over the grid bins: the B200 replacement for Meshes `search!`
+// on a KNearestSearch / KBallSearch (reference src/models.jl:153-164).
+//
+// One thread per target.  Cells are visited in Chebyshev rings around the target's cell; a max-heap of
+// the best k candidates lives in shared memory with layout [slot][thread] so every lane owns one bank
+// pair and heap traffic is conflict-free whatever slot a lane touches.  The search stops when the
+// current k-th distance is strictly below the distance to the nearest unvisited cell face.
+// Total order: ascending (d2, original row); d2 = ((dx*dx+dy*dy)+dz*dz) with every op rounded once
+// (gsm_d2_key) so the selected SET is bit-identical to the oracle's brute-force lexsort.
+// Output per target: positions into the cell-sorted record array, ascending by that order.
+#include "gsm_internal.cuh"
+
+namespace {
+
+constexpr int KNN_THREADS = 128;
+
+struct Heap {
+  double* d;  // [k][KNN_THREADS]
+  int* p;     // [k][KNN_THREADS] positions into rec
+  int k;
+  __device__ __forceinline__ double& D(int i) { return d[i * KNN_THREADS]; }
+  __device__ __forceinline__ int& P(int i) { return p[i * KNN_THREADS]; }
+};
+
+// (d2a, rowa) < (d2b, rowb)?  Rows are only fetched on exact distance ties.
+__device__ __forceinline__ bool key_less(double da, int pa, double db, int pb, const int* __restrict__ sidx) {
+  if (da < db) return true;
+  if (da > db) return false;
+  return sidx[pa] < sidx[pb];
+}
+
+__device__ __forceinline__ void sift_down(Heap& hp, int i, int n, double d, int p, const int* __restrict__ sidx) {
+  // place (d,p) at the hole i of a max-heap of size n
+  for (;;) {
+    int c = 2 * i + 1;
+    if (c >= n) break;
+    double dc = hp.D(c);
+    int pc = hp.P(c);
+    if (c + 1 < n) {
+      double dr = hp.D(c + 1);
+      int pr = hp.P(c + 1);
+      if (key_less(dc, pc, dr, pr, sidx)) {
+        dc = dr;
+        pc = pr;
+        c = c + 1;
+      }
+    }
+    if (!key_less(d, p, dc, pc, sidx)) break;
+    hp.D(i) = dc;
+    hp.P(i) = pc;
+    i = c;
+  }
+  hp.D(i) = d;
+  hp.P(i) = p;
+}
+
+__device__ __forceinline__ void sift_up(Heap& hp, int i, double d, int p, const int* __restrict__ sidx) {
+  while (i > 0) {
+    int par = (i - 1) >> 1;
+    double dp = hp.D(par);
+    int pp = hp.P(par);
+    if (!key_less(dp, pp, d, p, sidx)) break;
+    hp.D(i) = dp;
+    hp.P(i) = pp;
+    i = par;
+  }
+  hp.D(i) = d;
+  hp.P(i) = p;
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int* __restrict__ out_pos, int* __restrict__ out_cnt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Heap hp;
+  hp.d = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
+  hp.p = reinterpret_cast<int*>(smem_raw + (size_t)k * KNN_THREADS * sizeof(double)) + threadIdx.x;
+  hp.k = k;
+
+  long long t = blockIdx.x * (long long)KNN_THREADS + threadIdx.x;
+  if (t >= tg.count) return;
+  double tx, ty, tz;
+  gsm_target_coords(tg, tg.first + t, tx, ty, tz);
+
+  const int* __restrict__ cs = b.cell_start;
+  const double4* __restrict__ rec = b.rec;
+  const int* __restrict__ sidx = b.sidx;
+  const double tc[3] = {tx, ty, tz};
+  int c0[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    int c = (int)floor((tc[d] - b.bbmin[d]) * b.inv_h);
+    c0[d] = min(max(c, 0), b.nc[d] - 1);
+  }
+
+  int cnt = 0;
+  double worst = 1e308 * 10.0;  // +inf
+  const int maxring = max(max(b.nc[0], b.nc[1]), b.nc[2]);
+
+  for (int ring = 0; ring <= maxring; ++ring) {
+    const int zlo = max(c0[2] - ring, 0), zhi = min(c0[2] + ring, b.nc[2] - 1);
+    const int ylo = max(c0[1] - ring, 0), yhi = min(c0[1] + ring, b.nc[1] - 1);
+    const int xlo = max(c0[0] - ring, 0), xhi = min(c0[0] + ring, b.nc[0] - 1);
+    for (int cz = zlo; cz <= zhi; ++cz) {
+      const bool zface = (cz == c0[2] - ring) || (cz == c0[2] + ring);
+      for (int cy = ylo; cy <= yhi; ++cy) {
+        const bool yface = (cy == c0[1] - ring) || (cy == c0[1] + ring);
+        const int rowbase = b.nc[0] * (cy + b.nc[1] * cz);
+        // on a z- or y-face of the shell the whole x-run belongs to the ring; otherwise only its two ends
+        int nseg, segx[2][2];
+        if (zface || yface || ring == 0) {
+          nseg = 1;
+          segx[0][0] = xlo;
+          segx[0][1] = xhi;
+        } else {
+          nseg = 0;
+          if (c0[0] - ring >= 0) {
+            segx[nseg][0] = segx[nseg][1] = c0[0] - ring;
+            nseg++;
+          }
+          if (c0[0] + ring <= b.nc[0] - 1) {
+            segx[nseg][0] = segx[nseg][1] = c0[0] + ring;
+            nseg++;
+          }
+        }
+        for (int s = 0; s < nseg; ++s) {
+          const int beg = cs[rowbase + segx[s][0]];
+          const int end = cs[rowbase + segx[s][1] + 1];
+          for (int q = beg; q < end; ++q) {
+            const double4 r = rec[q];
+            const double d2 = gsm_d2_key(r.x, r.y, r.z, tx, ty, tz);
+            if (cnt < k) {
+              sift_up(hp, cnt, d2, q, sidx);
+              cnt++;
+              if (cnt == k) worst = hp.D(0);
+            } else if (d2 <= worst) {
+              if (key_less(d2, q, hp.D(0), hp.P(0), sidx)) {
+                sift_down(hp, 0, k, d2, q, sidx);
+                worst = hp.D(0);
+              }
+            }
+          }
+        }
+      }
+    }
+    // distance from the target to the nearest face that still has unvisited cells behind it
+    double reach = 1e308 * 10.0;
+    bool any = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (c0[d] - ring > 0) {
+        reach = fmin(reach, tc[d] - (b.bbmin[d] + (double)(c0[d] - ring) * b.h));
+        any = true;
+      }
+      if (c0[d] + ring < b.nc[d] - 1) {
+        reach = fmin(reach, (b.bbmin[d] + (double)(c0[d] + ring + 1) * b.h) - tc[d]);
+        any = true;
+      }
+    }
+    if (!any) break;  // every cell visited
+    if (cnt == k) {
+      // conservative margin: a sample can sit a rounding error outside its nominal cell box
+      double safe = reach - 1e-9 * b.h;
+      if (safe > 0.0 && worst < safe * safe) break;
+    }
+  }
+
+  // heap-sort in place: ascending (d2,row) ends up in slots 0..cnt-1
+  for (int n = cnt - 1; n > 0; --n) {
+    double dl = hp.D(n);
+    int pl = hp.P(n);
+    hp.D(n) = hp.D(0);
+    hp.P(n) = hp.P(0);
+    sift_down(hp, 0, n, dl, pl, sidx);
+  }
+  int nkeep = cnt;
+  if (radius > 0.0) {
+    // KBallSearch (models.jl:158): keep neighbours with distance <= radius (IEEE sqrt like the oracle)
+    nkeep = 0;
+    while (nkeep < cnt && __dsqrt_rn(hp.D(nkeep)) <= radius) nkeep++;
+  }
+  int* o = out_pos + t * (long long)k;
+  for (int i = 0; i < k; ++i) o[i] = i < nkeep ? hp.P(i) : -1;
+  out_cnt[t] = nkeep;
+}
+
+__global__ void pos_to_rows_kernel(const int* __restrict__ pos, long long total, const int* __restrict__ sidx,
+                                   int* __restrict__ rows) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int p = pos[i];
+  rows[i] = p >= 0 ? sidx[p] : -1;
+}
+
+}  // namespace
+
+int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt) {
+  if (tg.count <= 0) return GSM_OK;
+  size_t smem = (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int));
+  static size_t configured = 0;
+  if (smem > configured) {
+    GSM_CUDA(ctx, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  long long blocks = (tg.count + KNN_THREADS - 1) / KNN_THREADS;
+  knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, d_pos, d_cnt);
+  ctx->tim.launches++;
+  GSM_CUDA(ctx, cudaGetLastError());
+  return GSM_OK;
+}
+
+int gsm_launch_nbr_to_rows(gsm_ctx* ctx, const int* d_pos, long long total, int* d_rows) {
+  if (total <= 0) return GSM_OK;
+  pos_to_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_pos, total, ctx->bins.sidx, d_rows);
+  ctx->tim.launches++;
+  GSM_CUDA(ctx, cudaGetLastError());
+  return GSM_OK;
+}

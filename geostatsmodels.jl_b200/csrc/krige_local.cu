@@ -1,0 +1,276 @@
+// Batched local Kriging: for every target, gather its k neighbours, assemble the covariance system,
+// factor, solve, and emit mean and variance.  Replaces the per-target body of fitpredictneigh
+// (reference src/models.jl:162-184): fit (krig.jl:58-75: setlhs!/lhsfactorize!), weights
+// (krig.jl:316-339), krigmean (krig.jl:245-258, simple.jl:55-69) and predictvar (krig.jl:264-293).
+//
+// Formulation (one warp per system, k <= 32, lane r owns row r of the covariance block C):
+//   The reference factors the saddle-point matrix [C F; F' 0] with Bunch-Kaufman.  Here C (SPD) is
+//   Cholesky-factored in registers, and every right-hand side is forward-substituted in the same
+//   sweep:  u = L^-1 c0,  w = L^-1 z,  V = L^-1 F.  With  G = V'V,  g = V'u - f0,  G nu = g:
+//       mean = w'u - (V'w)' nu            variance = C0 - u'u + g' nu + 1e-10
+//   which equals lambda'z and C0 - c0'lambda - f0'nu of the reference (block elimination of the same
+//   system), so no back-substitution and no explicit weights are needed.
+//   Drift monomials are evaluated on coordinates centred at the target and scaled by the neighbourhood
+//   radius when the exponent set is a lower set (then the spanned polynomial space, hence the
+//   prediction, is unchanged while G stays well conditioned); otherwise on the raw coordinates.
+#include "gsm_internal.cuh"
+
+namespace {
+
+constexpr int LK_WARPS = 4;
+constexpr int LK_THREADS = LK_WARPS * 32;
+constexpr int LK_LD = 34;  // padded leading dimension of the per-warp covariance tile (doubles)
+
+struct WarpSmem {
+  double C[32 * LK_LD];
+  double l[32];
+  double px[32], py[32], pz[32];
+};
+
+template <int NCON>
+__global__ void __launch_bounds__(LK_THREADS, 4)
+local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int minn, int centered,
+                   const int* __restrict__ pos, const int* __restrict__ cnt, double* __restrict__ out_mean,
+                   double* __restrict__ out_var, unsigned char* __restrict__ out_status) {
+  __shared__ __align__(16) WarpSmem smem[LK_WARPS];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long t = blockIdx.x * (long long)LK_WARPS + warp;
+  if (t >= tg.count) return;
+  WarpSmem& sm = smem[warp];
+  constexpr int NR = 2 + NCON;  // right-hand sides: c0, z, drift columns
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+  const int n = cnt[t];
+  if (n < minn || n <= 0) {
+    if (lane == 0) {
+      out_mean[t] = qnan;
+      if (out_var) out_var[t] = qnan;
+      if (out_status) out_status[t] = GSM_ST_MISSING;
+    }
+    return;
+  }
+  double tx, ty, tz;
+  gsm_target_coords(tg, tg.first + t, tx, ty, tz);
+
+  // ---- gather ------------------------------------------------------------------------------
+  const bool live = lane < n;
+  double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (live) r = b.rec[pos[t * (long long)k + lane]];
+  sm.px[lane] = r.x;
+  sm.py[lane] = r.y;
+  sm.pz[lane] = r.z;
+  __syncwarp();
+
+  // ---- assemble C (covariance form), half the pairs per lane, mirrored through shared memory --
+  sm.C[lane * LK_LD + lane] = live ? v.sill : 1.0;
+#pragma unroll 4
+  for (int s = 1; s <= 16; ++s) {
+    const int c = (lane + s) & 31;
+    double val = 0.0;
+    if (live && c < n) {
+      const double dx = r.x - sm.px[c], dy = r.y - sm.py[c], dz = r.z - sm.pz[c];
+      val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+    }
+    sm.C[lane * LK_LD + c] = val;
+    sm.C[c * LK_LD + lane] = val;
+  }
+  __syncwarp();
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) {
+    const double2 p2 = *reinterpret_cast<const double2*>(&sm.C[lane * LK_LD + c]);
+    a[c] = p2.x;
+    a[c + 1] = p2.y;
+  }
+
+  // ---- right-hand sides ----------------------------------------------------------------------
+  double rhs[NR];
+  double d2t = 0.0;
+  {
+    const double dx = r.x - tx, dy = r.y - ty, dz = r.z - tz;
+    d2t = dx * dx + dy * dy + dz * dz;
+    rhs[0] = live ? gsm_cov_d2(v, d2t) : 0.0;
+    rhs[1] = live ? (NCON == 0 ? r.w - m.mean : r.w) : 0.0;
+  }
+  double f0[NCON > 0 ? NCON : 1];
+  if (NCON > 0) {
+    double ox = 0.0, oy = 0.0, oz = 0.0, isc = 1.0;
+    if (centered) {
+      double dmax = live ? d2t : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, gsm_shfl_xor(dmax, o));
+      isc = dmax > 0.0 ? rsqrt(dmax) : 1.0;
+      ox = tx;
+      oy = ty;
+      oz = tz;
+    }
+    const double sx = (r.x - ox) * isc, sy = (r.y - oy) * isc, sz = (r.z - oz) * isc;
+    const double gx = (tx - ox) * isc, gy = (ty - oy) * isc, gz = (tz - oz) * isc;
+#pragma unroll
+    for (int q = 0; q < NCON; ++q) {
+      rhs[2 + q] = live ? gsm_drift(m, q, sx, sy, sz) : 0.0;
+      f0[q] = gsm_drift(m, q, gx, gy, gz);
+    }
+  }
+
+  // ---- Cholesky of C with fused forward substitution ----------------------------------------
+  bool singular = false;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    double d = gsm_shfl(a[j], j);
+    if (!(d > 0.0)) {
+      singular = true;
+      d = 1.0;
+    }
+    const double rs = rsqrt(d);
+    const double l = (lane > j) ? a[j] * rs : 0.0;  // L[r][j], r > j
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+      const double yj = gsm_shfl(rhs[q], j) * rs;  // y_j = b_j / L_jj
+      rhs[q] = (lane == j) ? yj : fma(-l, yj, rhs[q]);
+    }
+    if (j < 31) {
+      sm.l[lane] = l;
+      __syncwarp();
+#pragma unroll
+      for (int cp = ((j + 1) >> 1) << 1; cp < 32; cp += 2) {
+        const double2 l2 = *reinterpret_cast<const double2*>(&sm.l[cp]);
+        if (cp > j) a[cp] = fma(-l, l2.x, a[cp]);
+        a[cp + 1] = fma(-l, l2.y, a[cp + 1]);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- inner products, Schur complement, outputs ---------------------------------------------
+  const double uu = gsm_warp_sum(rhs[0] * rhs[0]);
+  const double wu = gsm_warp_sum(rhs[1] * rhs[0]);
+  double mean, var;
+  const double c0 = v.sill;  // covzero for a point target: sill - gamma(0)  (krig.jl:295-301)
+  if (NCON == 0) {
+    mean = m.mean + wu;
+    var = c0 - uu;
+  } else {
+    double G[NCON > 0 ? NCON * NCON : 1];
+    double g[NCON > 0 ? NCON : 1], hw[NCON > 0 ? NCON : 1];
+#pragma unroll
+    for (int p = 0; p < NCON; ++p) {
+      g[p] = gsm_warp_sum(rhs[2 + p] * rhs[0]) - f0[p];
+      hw[p] = gsm_warp_sum(rhs[2 + p] * rhs[1]);
+#pragma unroll
+      for (int q = 0; q <= p; ++q) G[p * NCON + q] = gsm_warp_sum(rhs[2 + p] * rhs[2 + q]);
+    }
+    // Cholesky of G (every lane redundantly, registers), solve G nu = g
+#pragma unroll
+    for (int j = 0; j < NCON; ++j) {
+      double d = G[j * NCON + j];
+      if (!(d > 0.0)) {
+        singular = true;
+        d = 1.0;
+      }
+      const double rs = rsqrt(d);
+      G[j * NCON + j] = rs;  // store 1/L_jj
+#pragma unroll
+      for (int i = j + 1; i < NCON; ++i) G[i * NCON + j] *= rs;
+#pragma unroll
+      for (int i = j + 1; i < NCON; ++i)
+#pragma unroll
+        for (int q = j + 1; q <= i; ++q) G[i * NCON + q] = fma(-G[i * NCON + j], G[q * NCON + j], G[i * NCON + q]);
+    }
+    double y[NCON > 0 ? NCON : 1], hy[NCON > 0 ? NCON : 1];
+    // forward-substitute both g and hw:  nu'g = |L^-1 g|^2 ,  hw'nu = (L^-1 hw)'(L^-1 g)
+#pragma unroll
+    for (int i = 0; i < NCON; ++i) {
+      double s1 = g[i], s2 = hw[i];
+#pragma unroll
+      for (int q = 0; q < i; ++q) {
+        s1 = fma(-G[i * NCON + q], y[q], s1);
+        s2 = fma(-G[i * NCON + q], hy[q], s2);
+      }
+      y[i] = s1 * G[i * NCON + i];
+      hy[i] = s2 * G[i * NCON + i];
+    }
+    double gnu = 0.0, hnu = 0.0;
+#pragma unroll
+    for (int i = 0; i < NCON; ++i) {
+      gnu = fma(y[i], y[i], gnu);
+      hnu = fma(hy[i], y[i], hnu);
+    }
+    mean = wu - hnu;
+    var = c0 - uu + gnu;
+  }
+  var += 1e-10;  // krig.jl:278-279
+  if (lane == 0) {
+    out_mean[t] = singular ? qnan : mean;
+    if (out_var) out_var[t] = singular ? qnan : var;
+    if (out_status) out_status[t] = singular ? GSM_ST_SINGULAR : GSM_ST_OK;
+  }
+}
+
+template <int NCON>
+int launch(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k, int minn, int centered,
+           const int* pos, const int* cnt, double* mean, double* var, unsigned char* status) {
+  long long blocks = (tg.count + LK_WARPS - 1) / LK_WARPS;
+  local_krige_kernel<NCON><<<(unsigned)blocks, LK_THREADS, 0, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
+                                                                            pos, cnt, mean, var, status);
+  ctx->tim.launches++;
+  GSM_CUDA(ctx, cudaGetLastError());
+  return GSM_OK;
+}
+
+// exponent set closed under decrement => monomial span is translation invariant
+bool is_lower_set(const ModelDev& m) {
+  for (int a = 0; a < m.ndrift; ++a)
+    for (int d = 0; d < 3; ++d) {
+      if (m.exps[a][d] == 0) continue;
+      int e[3] = {m.exps[a][0], m.exps[a][1], m.exps[a][2]};
+      e[d]--;
+      bool found = false;
+      for (int c = 0; c < m.ndrift; ++c)
+        if (m.exps[c][0] == e[0] && m.exps[c][1] == e[1] && m.exps[c][2] == e[2]) found = true;
+      if (!found) return false;
+    }
+  return true;
+}
+
+}  // namespace
+
+int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in, const TargetsDev& tg, int k,
+                           int minneighbors, const int* d_pos, const int* d_cnt, double* d_mean, double* d_var,
+                           unsigned char* d_status) {
+  if (tg.count <= 0) return GSM_OK;
+  if (k > 32) {
+    gsm_set_error(ctx, "local Kriging kernel supports maxneighbors <= 32 in this build");
+    return GSM_ERR_UNSUPPORTED;
+  }
+  ModelDev m = m_in;
+  int ncon = 0;
+  if (m.kind == GSM_KRIG_ORDINARY) {  // OK == UK with the single constant drift (ordinary.jl:33-77)
+    ncon = 1;
+    m.ndrift = 1;
+    m.exps[0][0] = m.exps[0][1] = m.exps[0][2] = 0;
+  } else if (m.kind == GSM_KRIG_UNIVERSAL) {
+    ncon = m.ndrift;
+  }
+  const int centered = (ncon > 0 && is_lower_set(m)) ? 1 : 0;
+#define GSM_LK_CASE(N) \
+  case N:              \
+    return launch<N>(ctx, v, m, tg, k, minneighbors, centered, d_pos, d_cnt, d_mean, d_var, d_status);
+  switch (ncon) {
+    GSM_LK_CASE(0)
+    GSM_LK_CASE(1)
+    GSM_LK_CASE(2)
+    GSM_LK_CASE(3)
+    GSM_LK_CASE(4)
+    GSM_LK_CASE(5)
+    GSM_LK_CASE(6)
+    GSM_LK_CASE(7)
+    GSM_LK_CASE(8)
+    GSM_LK_CASE(9)
+    GSM_LK_CASE(10)
+  }
+#undef GSM_LK_CASE
+  gsm_set_error(ctx, "unsupported number of drift functions");
+  return GSM_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,169 @@
+/*
+ * gsm_b200.h -- C ABI of the B200-native interpolation hot path for the GeoStatsModels.jl API.
+ *
+ * Plain C: POD structs, raw pointers + sizes, `int` status returns (0 = ok), no exceptions, no
+ * torch / CUDA types in any signature.  This is exactly what a Julia `ccall` (or ctypes / cgo) binds.
+ * Every entry point names the reference interface it replaces (paths under JuliaEarth/GeoStatsModels.jl
+ * v0.13.10, `src/`).  The library is single-device per context: one process (or one context) per GPU.
+ *
+ * Coordinates handed to the library are ALREADY scaled by the caller with the alpha of
+ * models.jl:272-284 (`_scale`), exactly as the reference scales data, domain and variogram range before
+ * calling fitpredictneigh / fitpredictfull (models.jl:118).  The shim in INTEGRATION.md shows how.
+ *
+ * Pointer arguments documented as "host or device" are classified with cudaPointerGetAttributes;
+ * pinned host memory (gsm_host_alloc) makes the copies asynchronous DMA.
+ */
+#ifndef GSM_B200_H
+#define GSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GSM_API __attribute__((visibility("default")))
+#else
+#define GSM_API
+#endif
+
+#define GSM_ABI_VERSION 1
+#define GSM_MAX_DIM 3
+#define GSM_MAX_DRIFT 10   /* UniversalKriging(fun, deg=2, dim=3) -> 10 monomials (universal.jl:54-77) */
+#define GSM_MAX_NEIGHBORS 64
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+  GSM_OK = 0,
+  GSM_ERR_INVALID = 1,      /* bad argument (mirrors ArgumentError / @assert in the reference)   */
+  GSM_ERR_CUDA = 2,         /* CUDA runtime error, see gsm_last_error                              */
+  GSM_ERR_NO_SAMPLES = 3,   /* gsm_set_samples not called                                          */
+  GSM_ERR_UNSUPPORTED = 4,  /* signature the GPU path does not claim (falls to the generic Julia method) */
+  GSM_ERR_SINGULAR = 5      /* global factorisation failed: status(fitted) == false (krig.jl:49-52) */
+};
+
+/* per-target status byte written to out_status (models.jl:178-181; krig.jl:152 check=false) */
+enum {
+  GSM_ST_OK = 0,
+  GSM_ST_MISSING = 1,   /* fewer than minneighbors found -> `missing`               */
+  GSM_ST_SINGULAR = 2   /* non-positive pivot in the local system -> NaN outputs    */
+};
+
+/* ---- descriptors (POD) -------------------------------------------------------------------- */
+
+/* GeoStatsFunctions variogram, isotropic, Euclidean metric ball (call sites krig.jl:125,347,297).
+ * gamma(h), t = h/range:
+ *   GAUSSIAN     (sill-nugget)(1-exp(-3t^2)) + (h>0)(nugget+1e-6)
+ *   SPHERICAL    (sill-nugget)(1.5t-0.5t^3) for h<range, (sill-nugget) otherwise, + (h>0) nugget
+ *   EXPONENTIAL  (sill-nugget)(1-exp(-3t)) + (h>0) nugget
+ * The system is assembled in covariance form sill - gamma(h) (krig.jl:165-179, 364-378). */
+enum { GSM_VARIO_GAUSSIAN = 0, GSM_VARIO_SPHERICAL = 1, GSM_VARIO_EXPONENTIAL = 2 };
+typedef struct gsm_variogram {
+  int32_t kind;
+  int32_t _pad;
+  double sill;    /* total sill                         */
+  double nugget;
+  double range;   /* ALREADY multiplied by alpha        */
+} gsm_variogram;
+
+/* Kriging variant: SimpleKriging (simple.jl:29-69), OrdinaryKriging (ordinary.jl:25-77),
+ * UniversalKriging built by (deg, dim) (universal.jl:45-137): drift n at point x is
+ * prod_d x[d]^exps[n][d] on the scaled raw coordinates. */
+enum { GSM_KRIG_SIMPLE = 0, GSM_KRIG_ORDINARY = 1, GSM_KRIG_UNIVERSAL = 2 };
+typedef struct gsm_model {
+  int32_t kind;
+  int32_t ndrift;                         /* UK only, 1..GSM_MAX_DRIFT                    */
+  double mean;                            /* SK only (simple.jl:55-69)                    */
+  int32_t exps[GSM_MAX_DRIFT][GSM_MAX_DIM];
+} gsm_model;
+
+/* Target domain: a CartesianGrid (centroid of element (i0,j0,k0), 0-based, i fastest:
+ * (origin[d] + i_d*spacing[d]) + spacing[d]/2, every operation rounded once) or an explicit
+ * PointSet (npoints x dim doubles, AoS = memory order of a Julia Vector{Point}).
+ * [first, first+count) selects the shard of the linear target index this call predicts
+ * (models.jl:236-247 chunks the same index range over threads); count < 0 means "to the end". */
+enum { GSM_TARGETS_GRID = 0, GSM_TARGETS_POINTS = 1 };
+typedef struct gsm_targets {
+  int32_t kind;
+  int32_t dim;
+  double origin[GSM_MAX_DIM];    /* scaled */
+  double spacing[GSM_MAX_DIM];   /* scaled */
+  int64_t dims[GSM_MAX_DIM];
+  const double* points;          /* host or device, scaled; GSM_TARGETS_POINTS only */
+  int64_t npoints;
+  int64_t first;
+  int64_t count;
+} gsm_targets;
+
+/* Options of fitpredictneigh (models.jl:131-198). */
+typedef struct gsm_neighbor_opts {
+  int32_t maxneighbors;   /* clamped like models.jl:144-147 (outside [1,N] -> N, capped at GSM_MAX_NEIGHBORS) */
+  int32_t minneighbors;   /* clamped like models.jl:148-150                                        */
+  double radius;          /* > 0: KBallSearch with this (scaled) ball radius (models.jl:158); <= 0: KNearestSearch */
+} gsm_neighbor_opts;
+
+/* Per-phase device times of the last call on a context (CUDA events on the library's stream). */
+typedef struct gsm_timings {
+  double h2d_ms;       /* sample / target upload                               */
+  double bin_ms;       /* grid-bin build (KNearestSearch construction analogue) */
+  double knn_ms;       /* neighbour search kernel(s)                            */
+  double solve_ms;     /* assemble + factor + solve kernel(s)                   */
+  double d2h_ms;       /* result download                                       */
+  double total_ms;     /* first event to last event                             */
+  int64_t launches;    /* kernels launched by the library in the call           */
+} gsm_timings;
+
+typedef struct gsm_ctx gsm_ctx;   /* opaque; owns a device, a stream, sample + scratch buffers */
+typedef struct gsm_fit gsm_fit;   /* opaque; a fitted global Kriging model (FittedKriging)     */
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+GSM_API int gsm_abi_version(void);
+GSM_API int gsm_create(int device, gsm_ctx** out);
+GSM_API int gsm_destroy(gsm_ctx* ctx);
+/* Message of the last error on this context (or of the last failed gsm_create when ctx == NULL). */
+GSM_API const char* gsm_last_error(const gsm_ctx* ctx);
+GSM_API int gsm_get_timings(const gsm_ctx* ctx, gsm_timings* out);
+GSM_API int gsm_synchronize(gsm_ctx* ctx);
+
+/* Pinned host buffers so outputs DMA straight into caller-owned memory (Julia: unsafe_wrap). */
+GSM_API int gsm_host_alloc(void** out, int64_t bytes);
+GSM_API int gsm_host_free(void* p);
+
+/* ---- data: replaces `domain(dat)` / `values(dat)` of the geotable given to fit / fitpredict ----
+ * coords: n x dim doubles (AoS), values: n doubles; host or device; copied, never retained.
+ * Builds the grid bins used by the neighbour search (KNearestSearch construction, models.jl:155). */
+GSM_API int gsm_set_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values);
+
+/* ---- test hook: Meshes `search!` (models.jl:164).  out_idx: M x k int32 (0-based sample rows,
+ * ascending by (d2, index); unused slots = -1), out_n: M int32 neighbours found. host or device. */
+GSM_API int gsm_knn(gsm_ctx* ctx, const gsm_targets* targets, const gsm_neighbor_opts* opts,
+            int32_t* out_idx, int32_t* out_n);
+
+/* ---- fitpredictneigh with a Kriging model (models.jl:131-198 + krig.jl:58-75,316-339,245-293) --
+ * out_mean: M doubles.  out_var: M doubles or NULL (prob=false): sigma^2 INCLUDING the +1e-10 of
+ * krig.jl:278-279, i.e. the second field of the Normal that `_marginals` builds (models.jl:298-299).
+ * out_status: M bytes or NULL.  out_nbr: M x maxneighbors int32 or NULL.  All host or device. */
+GSM_API int gsm_local_krige(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_model* model,
+                    const gsm_targets* targets, const gsm_neighbor_opts* opts,
+                    double* out_mean, double* out_var, uint8_t* out_status, int32_t* out_nbr);
+
+/* ---- fit / predict / predictprob / status with all samples (krig.jl:58-75, 215-237, 49-52);
+ * fitpredictfull (models.jl:200-234) = fit once + predict over the domain. */
+GSM_API int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_model* model, gsm_fit** out);
+GSM_API int gsm_global_krige_status(const gsm_fit* fit);   /* 1 = factorisation succeeded */
+GSM_API int gsm_global_krige_predict(gsm_fit* fit, const gsm_targets* targets, double* out_mean, double* out_var);
+GSM_API int gsm_global_krige_free(gsm_fit* fit);
+
+/* ---- IDW (idw.jl:43-89): weights 1/d^exponent; exact hits return the first zero-distance sample.
+ * opts == NULL or opts->maxneighbors == 0: all samples (fitpredictfull); else local (fitpredictneigh). */
+GSM_API int gsm_idw(gsm_ctx* ctx, double exponent, const gsm_targets* targets, const gsm_neighbor_opts* opts,
+            double* out_mean, uint8_t* out_status);
+
+/* ---- measurement helper: sustained FP64 FMA throughput of this device in TFLOP/s (roofline peak) */
+GSM_API int gsm_measure_fp64_peak(gsm_ctx* ctx, double* out_dfma_tflops, double* out_dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSM_B200_H */

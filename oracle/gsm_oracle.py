@@ -1,0 +1,396 @@
+"""CPU oracle for the GeoStatsModels.jl interpolation hot path (TEST INFRASTRUCTURE ONLY).
+
+This module is a numpy/scipy restatement of the reference algorithm.  It is the *checker*:
+only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
+of ``bench.py`` may import it.  The product path (``geostatsmodels.jl_b200``) never does.
+
+PARITY PINNING
+  * Pinned against every numeric golden value the reference's own tests hold for this path
+    (``test/krig.jl:451-479`` docstring known-answers, ``test/misc.jl:2-25``, ``test/idw.jl``
+    exact-hit behaviour) -- see ``tests/test_oracle_golden.py``.
+  * **Parity unpinned** for: (1) interior variogram curve values (every golden sits at h = 0 or
+    h >= range), (2) neighbour tie-breaking, (3) the exact centroid arithmetic of a scaled
+    ``CartesianGrid``, (4) the GeoStatsFunctions / Meshes arithmetic in general -- those packages are
+    NOT vendored under /root/reference (Project.toml:26,29: GeoStatsFunctions "0.15", Meshes "0.57";
+    no Manifest is committed) and Julia is not installed, so their published formulas are restated
+    here from the documentation and every such choice is a named function below.
+
+Reference files followed (all paths under /root/reference):
+  src/models.jl:102-129   fitpredict            -> fitpredict()
+  src/models.jl:131-198   fitpredictneigh       -> _fitpredict_neigh()
+  src/models.jl:200-234   fitpredictfull        -> _fitpredict_full()
+  src/models.jl:272-296   _scale/_scalefactor   -> scale_factor()
+  src/krig.jl:58-75       fit                   -> KrigingSystem.__init__
+  src/krig.jl:111-138     setlhs!               -> KrigingSystem._setlhs
+  src/krig.jl:148-162     _lhsfactorize!        -> scipy dsytrf (upper), = bunchkaufman!(Symmetric(LHS))
+  src/krig.jl:165-179     lhsbanded!            -> covariance form  sill - gamma
+  src/krig.jl:316-361     weights/setrhs!       -> KrigingSystem.weights
+  src/krig.jl:245-258     krigmean              -> KrigingSystem.mean
+  src/krig.jl:264-313     predictvar/krigvar    -> KrigingSystem.variance (+1e-10)
+  src/krig/simple.jl:49-69, ordinary.jl:31-77, universal.jl:54-137 -> constraint blocks
+  src/idw.jl:59-89        idw/weights           -> idw_predict()
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.linalg import lapack
+
+# ----------------------------------------------------------------------------------------------
+# Variograms (GeoStatsFunctions 0.15, restated; call sites krig.jl:12,100,125,128,167,297,347)
+# ----------------------------------------------------------------------------------------------
+GAUSSIAN, SPHERICAL, EXPONENTIAL = 0, 1, 2
+_KIND_NAMES = {"gaussian": GAUSSIAN, "spherical": SPHERICAL, "exponential": EXPONENTIAL}
+
+# GaussianVariogram adds a small epsilon to the nugget "for numerical stability" (restated from
+# GeoStatsFunctions; unpinned by any reference test).  One switch so it can be corrected in one place.
+GAUSSIAN_NUGGET_EPS = 1e-6
+
+
+@dataclass(frozen=True)
+class Variogram:
+    kind: int
+    sill: float = 1.0
+    nugget: float = 0.0
+    range: float = 1.0
+
+    def scaled(self, alpha: float) -> "Variogram":
+        # GeoStatsFunctions.scale(fun, alpha): the metric-ball radius is multiplied by alpha
+        return Variogram(self.kind, self.sill, self.nugget, alpha * self.range)
+
+
+def variogram(v: Variogram, h):
+    """gamma(h) for an isotropic variogram with total sill ``sill``, nugget and range."""
+    h = np.asarray(h, dtype=np.float64)
+    s, n, r = v.sill, v.nugget, v.range
+    if v.kind == GAUSSIAN:
+        t = h / r
+        return (s - n) * (1.0 - np.exp(-3.0 * (t * t))) + (h > 0) * (n + GAUSSIAN_NUGGET_EPS)
+    if v.kind == SPHERICAL:
+        t = h / r
+        poly = (s - n) * (1.5 * t - 0.5 * (t * t * t))
+        return np.where(h < r, poly, (s - n)) + (h > 0) * n
+    if v.kind == EXPONENTIAL:
+        t = h / r
+        return (s - n) * (1.0 - np.exp(-3.0 * t)) + (h > 0) * n
+    raise ValueError("unknown variogram kind")
+
+
+def covariance(v: Variogram, h):
+    """Covariance form used for stationary variograms: sill - gamma(h) (krig.jl:165-179, 364-378)."""
+    return v.sill - variogram(v, h)
+
+
+def pairdist(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """Euclidean distance matrix |a_i - b_j|, summed in dimension order (no FMA in numpy)."""
+    d2 = np.zeros((A.shape[0], B.shape[0]))
+    for d in range(A.shape[1]):
+        diff = A[:, d][:, None] - B[:, d][None, :]
+        d2 = d2 + diff * diff
+    return np.sqrt(d2)
+
+
+# ----------------------------------------------------------------------------------------------
+# Models (krig/simple.jl, krig/ordinary.jl, krig/universal.jl, idw.jl)
+# ----------------------------------------------------------------------------------------------
+SK, OK, UK = 0, 1, 2
+
+
+def monomial_exponents(deg: int, dim: int) -> list[tuple[int, ...]]:
+    """universal.jl:68-77 ``exponents``: multiexponents(dim, d) for d = 0..deg (lexicographically
+    descending within a degree, as Combinatorics enumerates them), then a STABLE sort by maximum
+    exponent, descending."""
+    assert deg >= 0 and dim > 0
+    cols: list[tuple[int, ...]] = []
+    for d in range(deg + 1):
+        exps = [e for e in itertools.product(range(d, -1, -1), repeat=dim) if sum(e) == d]
+        cols.extend(exps)  # itertools.product with descending ranges == lexicographic descending
+    order = sorted(range(len(cols)), key=lambda i: -max(cols[i]))  # python sort is stable
+    return [cols[i] for i in order]
+
+
+@dataclass(frozen=True)
+class KrigingModel:
+    kind: int
+    vario: Variogram
+    mean: float = 0.0
+    exps: tuple = field(default_factory=tuple)  # UK monomial exponents, tuple of tuples
+
+    @property
+    def ncon(self) -> int:
+        return {SK: 0, OK: 1}.get(self.kind, len(self.exps))
+
+    def scaled(self, alpha: float) -> "KrigingModel":
+        return KrigingModel(self.kind, self.vario.scaled(alpha), self.mean, self.exps)
+
+
+def simple_kriging(vario, mean):
+    return KrigingModel(SK, vario, float(mean))
+
+
+def ordinary_kriging(vario):
+    return KrigingModel(OK, vario)
+
+
+def universal_kriging(vario, deg, dim):
+    return KrigingModel(UK, vario, 0.0, tuple(monomial_exponents(deg, dim)))
+
+
+def universal_kriging_exps(vario, exps):
+    return KrigingModel(UK, vario, 0.0, tuple(tuple(e) for e in exps))
+
+
+def drift_matrix(exps, X: np.ndarray) -> np.ndarray:
+    """F[e, n] = prod_d X[e, d] ** exps[n][d]  (universal.jl:60-62, integer powers by multiplication)."""
+    F = np.ones((X.shape[0], len(exps)))
+    for n, e in enumerate(exps):
+        col = np.ones(X.shape[0])
+        for d, p in enumerate(e):
+            xp = np.ones(X.shape[0])
+            for _ in range(p):
+                xp = xp * X[:, d]
+            col = col * xp
+        F[:, n] = col
+    return F
+
+
+# ----------------------------------------------------------------------------------------------
+# Kriging system: fit / weights / mean / variance (krig.jl)
+# ----------------------------------------------------------------------------------------------
+VAR_EPS = 1e-10  # krig.jl:278-279
+
+
+class KrigingSystem:
+    """FittedKriging for a univariate model on point data without missing values."""
+
+    def __init__(self, model: KrigingModel, X: np.ndarray, z: np.ndarray):
+        self.model = model
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.z = np.asarray(z, dtype=np.float64)
+        n = self.X.shape[0]
+        m = n + model.ncon
+        self.n, self.m = n, m
+        self.LHS = self._setlhs()
+        # bunchkaufman!(Symmetric(LHS), check=false)  == LAPACK dsytrf, uplo='U'
+        ldu, ipiv, info = lapack.dsytrf(self.LHS, lower=0)
+        self._ldu, self._ipiv, self.info = ldu, ipiv, info
+
+    def status(self) -> bool:  # krig.jl:49-52
+        return self.info == 0
+
+    def _setlhs(self) -> np.ndarray:
+        model, X, n, m = self.model, self.X, self.n, self.m
+        LHS = np.zeros((m, m), order="F")
+        LHS[:n, :n] = covariance(model.vario, pairdist(X, X))  # pairwise! + lhsbanded!
+        if model.kind == OK:  # ordinary.jl:33-58
+            LHS[n, :n] = 1.0
+            LHS[:n, n] = 1.0
+        elif model.kind == UK:  # universal.jl:81-113
+            F = drift_matrix(model.exps, X)
+            LHS[n:, :n] = F.T
+            LHS[:n, n:] = F
+        return LHS
+
+    def rhs(self, x0: np.ndarray) -> np.ndarray:  # krig.jl:342-361
+        model, n, m = self.model, self.n, self.m
+        r = np.zeros(m)
+        r[:n] = covariance(model.vario, pairdist(self.X, x0[None, :])[:, 0])
+        if model.kind == OK:
+            r[n] = 1.0
+        elif model.kind == UK:
+            r[n:] = drift_matrix(model.exps, x0[None, :])[0]
+        return r
+
+    def weights(self, x0: np.ndarray):
+        r = self.rhs(np.asarray(x0, dtype=np.float64))
+        w, info = lapack.dsytrs(self._ldu, self._ipiv, r, lower=0)  # FHS \ RHS
+        return w, r
+
+    def predict(self, x0):
+        """(mean, variance) at x0: krigmean (krig.jl:245-258 / simple.jl:55-69), predictvar (264-293)."""
+        w, r = self.weights(x0)
+        n = self.n
+        lam, nu = w[:n], w[n:]
+        if self.model.kind == SK:
+            mu = self.model.mean + float(np.sum(lam * (self.z - self.model.mean)))
+        else:
+            mu = float(np.sum(lam * self.z))
+        c0 = self.model.vario.sill - float(variogram(self.model.vario, 0.0))  # covzero for a point
+        var = c0 - float(r[:n] @ lam) - float(r[n:] @ nu) + VAR_EPS
+        return mu, var
+
+
+# ----------------------------------------------------------------------------------------------
+# Domains, scaling (models.jl:265-296)
+# ----------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Grid:
+    """CartesianGrid(origin, spacing, dims): element (i0,j0,..) 0-based, linear index i fastest."""
+    origin: tuple
+    spacing: tuple
+    dims: tuple
+
+    @property
+    def dim(self):
+        return len(self.dims)
+
+    @property
+    def nelements(self):
+        return int(np.prod(self.dims))
+
+    def bbox_absmax(self) -> float:
+        lo = np.asarray(self.origin, dtype=np.float64)
+        hi = lo + np.asarray(self.dims, dtype=np.float64) * np.asarray(self.spacing, dtype=np.float64)
+        return float(max(np.abs(lo).max(), np.abs(hi).max()))
+
+    def scaled(self, alpha: float) -> "Grid":
+        return Grid(tuple(alpha * np.asarray(self.origin, dtype=np.float64)),
+                    tuple(alpha * np.asarray(self.spacing, dtype=np.float64)), self.dims)
+
+    def centroids(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        """DECLARED CHOICE: centroid = (origin + i0 * spacing) + spacing / 2, each op rounded once."""
+        count = self.nelements - first if count is None else count
+        lin = np.arange(first, first + count, dtype=np.int64)
+        out = np.empty((count, self.dim))
+        for d in range(self.dim):
+            i0 = lin % self.dims[d]
+            lin = lin // self.dims[d]
+            o, s = np.float64(self.origin[d]), np.float64(self.spacing[d])
+            out[:, d] = (o + i0.astype(np.float64) * s) + s / 2.0
+        return out
+
+
+def points_absmax(P: np.ndarray) -> float:
+    return float(np.abs(P).max())
+
+
+def scale_factor(model_range: float, data_absmax: float, dom_absmax: float) -> float:
+    """alpha of models.jl:272-284; an infinite model range counts as 1 (models.jl:293-296)."""
+    a1 = 1.0 if np.isinf(model_range) else model_range
+    return 1.0 / max(a1, data_absmax, dom_absmax)
+
+
+# ----------------------------------------------------------------------------------------------
+# k-nearest neighbours (Meshes KNearestSearch / KBallSearch; DECLARED tie-break)
+# ----------------------------------------------------------------------------------------------
+def sqdist_keys(X: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """d2 = ((dx*dx + dy*dy) + dz*dz): dimension order, every op rounded (no FMA)."""
+    d2 = np.zeros(X.shape[0])
+    for d in range(X.shape[1]):
+        diff = X[:, d] - t[d]
+        d2 = d2 + diff * diff
+    return d2
+
+
+def knn(X: np.ndarray, t: np.ndarray, k: int, radius: float | None = None):
+    """Exact k nearest rows of X to t, ascending by the total order (d2, index).
+    With ``radius`` (KBallSearch, models.jl:158) neighbours with distance > radius are dropped."""
+    d2 = sqdist_keys(X, t)
+    order = np.lexsort((np.arange(X.shape[0]), d2))[:k]
+    if radius is not None:
+        order = order[d2[order] <= radius * radius]
+    return order.astype(np.int64)
+
+
+# ----------------------------------------------------------------------------------------------
+# IDW (idw.jl:59-89)
+# ----------------------------------------------------------------------------------------------
+def idw_predict(X: np.ndarray, z: np.ndarray, x0: np.ndarray, exponent) -> float:
+    d = np.sqrt(sqdist_keys(X, x0))
+    with np.errstate(divide="ignore"):
+        if float(exponent).is_integer():
+            p = np.ones_like(d)
+            for _ in range(int(exponent)):  # integer power by repeated multiplication
+                p = p * d
+            w = 1.0 / p
+        else:
+            w = 1.0 / d ** float(exponent)
+    sw = np.sum(w)
+    if np.isinf(sw):  # some distance is zero -> value of the FIRST such sample (idw.jl:68-69)
+        return float(z[np.flatnonzero(np.isinf(w))[0]])
+    return float(np.sum((w / sw) * z))
+
+
+# ----------------------------------------------------------------------------------------------
+# fitpredict (models.jl:102-249)
+# ----------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class IDWModel:
+    exponent: float = 1.0
+
+
+def _targets(dom, first=0, count=None) -> np.ndarray:
+    if isinstance(dom, Grid):
+        return dom.centroids(first, count)
+    P = np.asarray(dom, dtype=np.float64)
+    count = P.shape[0] - first if count is None else count
+    return P[first:first + count]
+
+
+def _dom_absmax(dom) -> float:
+    return dom.bbox_absmax() if isinstance(dom, Grid) else points_absmax(np.asarray(dom))
+
+
+def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, maxneighbors=10,
+               neighborhood=None, first=0, count=None, return_neighbors=False):
+    """Returns (mean[M], var[M] or None, status[M] uint8, [nbr list]).  status: 0 ok, 1 missing
+    (fewer than minneighbors found, models.jl:178-181), 2 factorisation failed."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    z = np.asarray(z, dtype=np.float64)
+    rng = model.vario.range if isinstance(model, KrigingModel) else np.inf
+    alpha = scale_factor(rng, points_absmax(X), _dom_absmax(dom))
+    smodel = model.scaled(alpha) if isinstance(model, KrigingModel) else model
+    sX = X * alpha
+    if isinstance(dom, Grid):
+        sT = _targets(dom.scaled(alpha), first, count)
+    else:
+        sT = _targets(np.asarray(dom, dtype=np.float64) * alpha, first, count)
+    srad = None if neighborhood is None else alpha * float(neighborhood)
+    M = sT.shape[0]
+    mean = np.full(M, np.nan)
+    var = np.full(M, np.nan) if prob else None
+    status = np.zeros(M, dtype=np.uint8)
+    nbrs = []
+    nobs = sX.shape[0]
+    if neighbors:
+        if maxneighbors > nobs or maxneighbors < 1:
+            maxneighbors = nobs
+        if minneighbors > maxneighbors or minneighbors < 1:
+            minneighbors = 1
+        for j in range(M):
+            idx = knn(sX, sT[j], maxneighbors, srad)
+            if return_neighbors:
+                nbrs.append(idx)
+            if len(idx) < minneighbors:
+                status[j] = 1
+                continue
+            mean[j], v, ok = _predict_one(smodel, sX[idx], z[idx], sT[j])
+            if prob:
+                var[j] = v
+            if not ok:
+                status[j] = 2
+    else:
+        if isinstance(smodel, KrigingModel):
+            ks = KrigingSystem(smodel, sX, z)
+            for j in range(M):
+                mean[j], v = ks.predict(sT[j])
+                if prob:
+                    var[j] = v
+            if not ks.status():
+                status[:] = 2
+        else:
+            for j in range(M):
+                mean[j] = idw_predict(sX, z, sT[j], smodel.exponent)
+    if return_neighbors:
+        return mean, var, status, nbrs
+    return mean, var, status
+
+
+def _predict_one(smodel, Xn, zn, x0):
+    if isinstance(smodel, KrigingModel):
+        ks = KrigingSystem(smodel, Xn, zn)
+        mu, v = ks.predict(x0)
+        return mu, v, ks.status()
+    return idw_predict(Xn, zn, x0, smodel.exponent), 0.0, True

@@ -1,0 +1,266 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200.
+
+Tolerances (BASELINE.json north_star): neighbour index lists bit-exact under the total order
+(d2, row); means and variances within relative 1e-10 in Float64.  `atol` below is the absolute floor
+for quantities that are differences of O(sill) terms (an exact-hit variance is 1e-10 + rounding)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+ATOL = 1e-12
+
+
+def _samples(seed, n, dim, extent):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, extent, size=(n, dim))
+    z = np.sin(X[:, 0] / 20) + np.cos(X[:, -1] / 30) + 0.1 * rng.standard_normal(n)
+    return X, z
+
+
+def _grid_targets(gsm, o, dims, alpha=1.0, origin=None, spacing=None):
+    origin = origin or tuple(0.0 for _ in dims)
+    spacing = spacing or tuple(1.0 for _ in dims)
+    og = o.Grid(origin, spacing, dims).scaled(alpha) if alpha != 1.0 else o.Grid(origin, spacing, dims)
+    t = gsm.Context.grid_targets(og.origin, og.spacing, dims)
+    return t, og
+
+
+# ------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("dim,n,k", [(2, 5000, 32), (3, 8000, 32), (2, 300, 8), (3, 4000, 64), (1, 500, 16)])
+def test_knn_lists_bit_exact(gsm, oracle, ctx, dim, n, k):
+    X, z = _samples(10 + dim, n, dim, 64.0)
+    ctx.set_samples(X, z)
+    dims = {1: (200,), 2: (40, 30), 3: (12, 10, 9)}[dim]
+    sp = tuple(64.0 / d for d in dims)
+    t, og = _grid_targets(gsm, oracle, dims, spacing=sp)
+    idx, cnt = ctx.knn(t, k)
+    T = og.centroids()
+    assert (cnt == k).all()
+    for j in range(T.shape[0]):
+        ref = oracle.knn(X, T[j], k)
+        assert np.array_equal(idx[j], ref), (j, idx[j], ref)
+
+
+def test_knn_ties_on_lattice_samples(gsm, oracle, ctx):
+    """Samples on an integer lattice, targets on lattice points and cell centres: massive distance ties."""
+    g = np.stack(np.meshgrid(np.arange(24.0), np.arange(24.0), indexing="ij"), -1).reshape(-1, 2)
+    rng = np.random.default_rng(5)
+    X = g[rng.permutation(len(g))]
+    z = rng.standard_normal(len(X))
+    ctx.set_samples(X, z)
+    P = np.concatenate([g[::7], g[::11] + 0.5])
+    t = gsm.Context.point_targets(P)
+    idx, cnt = ctx.knn(t, 16)
+    for j in range(len(P)):
+        assert np.array_equal(idx[j], oracle.knn(X, P[j], 16)), j
+
+
+def test_knn_targets_outside_bbox_and_ball(gsm, oracle, ctx):
+    X, z = _samples(3, 2000, 2, 50.0)
+    ctx.set_samples(X, z)
+    P = np.array([[-30.0, -30.0], [80.0, 10.0], [25.0, 200.0], [25.0, 25.0], [0.0, 0.0]])
+    idx, cnt = ctx.knn(gsm.Context.point_targets(P), 12)
+    for j in range(len(P)):
+        assert np.array_equal(idx[j], oracle.knn(X, P[j], 12))
+    idx, cnt = ctx.knn(gsm.Context.point_targets(P), 12, radius=2.0)   # KBallSearch
+    for j in range(len(P)):
+        ref = oracle.knn(X, P[j], 12, radius=2.0)
+        assert cnt[j] == len(ref)
+        assert np.array_equal(idx[j, :cnt[j]], ref)
+        assert (idx[j, cnt[j]:] == -1).all()
+
+
+def test_knn_fewer_samples_than_k(gsm, oracle, ctx):
+    X, z = _samples(4, 5, 2, 10.0)
+    ctx.set_samples(X, z)
+    P = np.array([[1.0, 1.0], [9.0, 2.0]])
+    idx, cnt = ctx.knn(gsm.Context.point_targets(P), 32)   # clamps to N (models.jl:144-147)
+    assert idx.shape == (2, 5) and (cnt == 5).all()
+    for j in range(2):
+        assert np.array_equal(idx[j], oracle.knn(X, P[j], 5))
+
+
+# --------------------------------------------------------------------------- local Kriging parity
+def _oracle_model(o, kind, vario, dim, mean=0.0, deg=None):
+    if kind == "sk":
+        return o.simple_kriging(vario, mean)
+    if kind == "ok":
+        return o.ordinary_kriging(vario)
+    return o.universal_kriging(vario, deg, dim)
+
+
+def _gsm_model(gsm, kind, vario, dim, mean=0.0, deg=None):
+    cls = {0: gsm.GaussianVariogram, 1: gsm.SphericalVariogram, 2: gsm.ExponentialVariogram}[vario.kind]
+    fun = cls(sill=vario.sill, range=vario.range, nugget=vario.nugget)
+    if kind == "sk":
+        return gsm.SimpleKriging(fun, mean)
+    if kind == "ok":
+        return gsm.OrdinaryKriging(fun)
+    return gsm.UniversalKriging(fun, deg, dim)
+
+
+CASES = [
+    # kind, vario kind, dim, deg, k
+    ("ok", 1, 2, None, 32),
+    ("sk", 1, 2, None, 32),
+    ("ok", 2, 2, None, 16),
+    ("ok", 0, 2, None, 12),
+    ("uk", 1, 2, 1, 32),
+    ("uk", 1, 2, 2, 32),
+    ("ok", 1, 3, None, 32),
+    ("uk", 1, 3, 1, 32),
+    ("uk", 1, 3, 2, 32),
+    ("sk", 2, 3, None, 8),
+]
+
+
+@pytest.mark.parametrize("kind,vk,dim,deg,k", CASES)
+def test_local_kriging_matches_oracle(gsm, oracle, kind, vk, dim, deg, k):
+    o = oracle
+    n = 3000 if dim == 2 else 6000
+    X, z = _samples(100 + vk + dim, n, dim, 100.0)
+    vario = o.Variogram(vk, 1.0, 0.1, 25.0)
+    om = _oracle_model(o, kind, vario, dim, mean=float(z.mean()), deg=deg)
+    gm = _gsm_model(gsm, kind, vario, dim, mean=float(z.mean()), deg=deg)
+    dims = (24, 20) if dim == 2 else (8, 7, 6)
+    sp = tuple(100.0 / d for d in dims)
+    mu, var, st = o.fitpredict(om, X, z, o.Grid(tuple(0.0 for _ in dims), sp, dims), maxneighbors=k, prob=True)
+    grid = gsm.CartesianGrid(tuple(0.0 for _ in dims), tuple(100.0 for _ in dims), dims=dims)
+    pred = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=k, prob=True)
+    got = pred.z
+    assert (st == 0).all()
+    assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL), np.abs(got.mu - mu).max()
+    assert np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL), np.abs(got.sigma - var).max()
+    pred2 = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=k, prob=False)
+    assert np.array_equal(pred2.z, got.mu)
+
+
+def test_local_kriging_golden_misc_jl(gsm):
+    """reference test/misc.jl:13-25 through the GPU path (neighbors=true; N=3 < maxneighbors)."""
+    data = gsm.georef({"z": np.array([1.0, 0.0, 1.0])}, [(25.0, 25.0), (50.0, 75.0), (75.0, 50.0)])
+    grid = gsm.CartesianGrid((0.5, 0.5), (100.5, 100.5), dims=(100, 100))
+    pred = gsm.fitpredict(gsm.Kriging(gsm.SphericalVariogram(range=35.0)), data, grid, neighbors=True)
+    lin = lambda i, j: (i - 1) + (j - 1) * 100
+    assert pred.z[lin(25, 25)] == pytest.approx(1.0, abs=1e-3)
+    assert pred.z[lin(50, 75)] == pytest.approx(0.0, abs=1e-3)
+    assert pred.z[lin(75, 50)] == pytest.approx(1.0, abs=1e-3)
+    assert pred.geometry == grid   # test/misc.jl:53-59
+
+
+def test_local_kriging_golden_docstrings(gsm, ctx):
+    """reference test/krig.jl:451-479 known answers, via the local kernel with all 3 samples as neighbours
+    (no rescaling: fit/predict are called directly in the reference test)."""
+    L = gsm._lib
+    X = np.array([[25.0, 25.0], [50.0, 75.0], [75.0, 50.0]])
+    t = gsm.Context.point_targets(np.array([[50.0, 50.0]]))
+    sph = L.make_variogram(L.GSM_VARIO_SPHERICAL, 1.0, 0.0, 1.0)
+    ctx.set_samples(X, np.array([1.0, 0.0, 0.0]))
+    mean, _, _, _ = ctx.local_krige(sph, L.make_model(L.GSM_KRIG_SIMPLE, mean=5.0), t, 3)
+    assert mean[0] == pytest.approx(5.0, rel=1e-14)
+    mean, _, _, _ = ctx.local_krige(sph, L.make_model(L.GSM_KRIG_ORDINARY), t, 3)
+    assert mean[0] == pytest.approx(1 / 3, rel=1e-14)
+    mean, _, _, _ = ctx.local_krige(sph, L.make_model(L.GSM_KRIG_UNIVERSAL, exps=[(0, 0), (1, 0), (0, 1)]), t, 3)
+    assert mean[0] == pytest.approx(1 / 3, rel=1e-12)
+    uk2 = L.make_model(L.GSM_KRIG_UNIVERSAL, exps=[(0, 0), (2, 0)])   # not a lower set: raw monomials
+    mean, _, _, _ = ctx.local_krige(sph, uk2, t, 3)
+    assert mean[0] == pytest.approx(0.4081632653061225, rel=1e-12)
+    ctx.set_samples(X, np.array([0.0, 1.0, 0.0]))
+    mean, _, _, _ = ctx.local_krige(sph, uk2, t, 3)
+    assert mean[0] == pytest.approx(0.34693877551020413, rel=1e-12)
+
+
+def test_local_kriging_properties(gsm, oracle):
+    """Property tests of reference test/krig.jl:29-126 restated against the GPU library."""
+    X, z = _samples(77, 4000, 2, 100.0)
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    fun = gsm.SphericalVariogram(range=30.0, sill=1.0, nugget=0.0)
+    sk = gsm.SimpleKriging(fun, float(z.mean()))
+    ok = gsm.OrdinaryKriging(fun)
+    # interpolation at sample locations, var >= 0, var(SK) <= var(OK)
+    P = gsm.PointSet(X[:200])
+    psk = gsm.fitpredict(sk, tab, P, maxneighbors=32, prob=True).z
+    pok = gsm.fitpredict(ok, tab, P, maxneighbors=32, prob=True).z
+    puk = gsm.fitpredict(gsm.UniversalKriging(fun, 1, 2), tab, P, maxneighbors=32, prob=True).z
+    for p in (psk, pok, puk):
+        assert np.allclose(p.mu, z[:200], rtol=1e-9, atol=1e-9)
+        assert (p.sigma >= 0).all()
+    assert (psk.sigma <= pok.sigma + 1e-12).all()
+    # OK == UK(deg 0)
+    Q = gsm.CartesianGrid((0.0, 0.0), (100.0, 100.0), dims=(16, 16))
+    a = gsm.fitpredict(ok, tab, Q, maxneighbors=32, prob=True).z
+    b = gsm.fitpredict(gsm.UniversalKriging(fun, 0, 2), tab, Q, maxneighbors=32, prob=True).z
+    assert np.allclose(a.mu, b.mu, rtol=1e-12) and np.allclose(a.sigma, b.sigma, rtol=1e-12)
+    # sill scaling: mean unchanged, variance (minus the 1e-10 floor) scales
+    fun2 = gsm.SphericalVariogram(range=30.0, sill=2.0, nugget=0.0)
+    c = gsm.fitpredict(gsm.OrdinaryKriging(fun2), tab, Q, maxneighbors=32, prob=True).z
+    assert np.allclose(c.mu, a.mu, rtol=1e-10)
+    assert np.allclose(c.sigma - 1e-10, 2.0 * (a.sigma - 1e-10), rtol=1e-9, atol=1e-12)
+    # variance is a function of the configuration, not of the values
+    tab2 = gsm.georef({"z": z + np.random.default_rng(1).uniform(size=len(z))}, gsm.PointSet(X))
+    d = gsm.fitpredict(ok, tab2, Q, maxneighbors=32, prob=True).z
+    assert np.array_equal(d.sigma, a.sigma)
+
+
+def test_minneighbors_missing_and_shards(gsm, oracle):
+    X, z = _samples(8, 1500, 2, 60.0)
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    ok = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=20.0, nugget=0.05))
+    P = np.concatenate([np.random.default_rng(2).uniform(0, 60, size=(64, 2)), [[500.0, 500.0]]])
+    pred = gsm.fitpredict(ok, tab, gsm.PointSet(P), maxneighbors=16, minneighbors=3, neighborhood=6.0, prob=True)
+    om = oracle.ordinary_kriging(oracle.Variogram(oracle.SPHERICAL, 1.0, 0.05, 20.0))
+    mu, var, st = oracle.fitpredict(om, X, z, P, maxneighbors=16, minneighbors=3, neighborhood=6.0, prob=True)
+    got = pred.z
+    miss = np.ma.getmaskarray(got.mu)
+    assert np.array_equal(miss, st == 1) and miss[-1]
+    assert np.allclose(np.ma.filled(got.mu, 0)[~miss], mu[~miss], rtol=RTOL, atol=ATOL)
+    assert np.allclose(np.ma.filled(got.sigma, 0)[~miss], var[~miss], rtol=RTOL, atol=ATOL)
+    # shards of a grid concatenate to the whole domain
+    grid = gsm.CartesianGrid((0.0, 0.0), (60.0, 60.0), dims=(20, 15))
+    whole = gsm.fitpredict(ok, tab, grid, maxneighbors=16).z
+    parts = [gsm.fitpredict(ok, tab, grid, maxneighbors=16, first=f, count=c).z for f, c in ((0, 100), (100, 77), (177, 123))]
+    assert np.array_equal(np.concatenate(parts), whole)
+
+
+# ------------------------------------------------------------------------------------------- IDW
+@pytest.mark.parametrize("exponent", [1, 2, 3, 2.5])
+def test_idw_global_matches_oracle(gsm, oracle, exponent):
+    X, z = _samples(21, 2000, 2, 256.0)
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    grid = gsm.CartesianGrid(24, 24)
+    pred = gsm.fitpredict(gsm.IDW(exponent), tab, grid, neighbors=False).z
+    mu, _, _ = oracle.fitpredict(oracle.IDWModel(exponent), X, z, oracle.Grid((0.0, 0.0), (1.0, 1.0), (24, 24)), neighbors=False)
+    assert np.allclose(pred, mu, rtol=RTOL, atol=ATOL), np.abs(pred - mu).max()
+
+
+def test_idw_local_and_exact_hits(gsm, oracle):
+    X, z = _samples(22, 3000, 3, 40.0)
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    P = np.concatenate([X[:50], np.random.default_rng(9).uniform(0, 40, size=(200, 3))])
+    pred = gsm.fitpredict(gsm.IDW(2), tab, gsm.PointSet(P), maxneighbors=10).z
+    mu, _, _ = oracle.fitpredict(oracle.IDWModel(2), X, z, P, maxneighbors=10)
+    assert np.allclose(pred, mu, rtol=RTOL, atol=ATOL)
+    assert np.array_equal(pred[:50], z[:50])   # exact hits return the sample value (test/idw.jl:9-16)
+    # test/misc.jl:2-8: IDW on its own point set reproduces the data exactly
+    data = gsm.georef({"z": np.array([1.0, 2.0, 3.0])}, [(25.0, 25.0), (50.0, 75.0), (75.0, 25.0)])
+    out = gsm.fitpredict(gsm.IDW(), data, data.domain, neighbors=False)
+    assert np.array_equal(out.z, data.z) and out.geometry == data.geometry
+
+
+def test_error_codes(gsm):
+    L = gsm._lib
+    c = gsm.Context(0)
+    t = gsm.Context.point_targets(np.zeros((1, 2)))
+    with pytest.raises(gsm.GsmError) as e:
+        c.idw(2.0, t)
+    assert e.value.code == L.GSM_ERR_NO_SAMPLES
+    c.set_samples(np.random.default_rng(0).uniform(size=(100, 2)), np.zeros(100))
+    with pytest.raises(gsm.GsmError) as e:
+        c.local_krige(L.make_variogram(7, 1, 0, 1), L.make_model(L.GSM_KRIG_ORDINARY), t, 8)
+    assert e.value.code == L.GSM_ERR_INVALID
+    with pytest.raises(gsm.GsmError) as e:
+        c.local_krige(L.make_variogram(1, 1, 0, 1), L.make_model(L.GSM_KRIG_ORDINARY),
+                      gsm.Context.point_targets(np.zeros((1, 3))), 8)
+    assert e.value.code == L.GSM_ERR_INVALID
+    c.close()
