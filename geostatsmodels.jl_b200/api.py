@@ -392,11 +392,12 @@ def _targets_for(dom, alpha, first=0, count=-1):
 
 def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=True, minneighbors=1,
                maxneighbors=10, neighborhood=None, distance="euclidean", device=None, first=0, count=-1,
-               ctx=None):
+               ctx=None, out=None):
     """fitpredict(model, geotable, domain; options) (models.jl:102-129).
 
     ``first``/``count`` (not in the reference) select a contiguous shard of the target index for
-    multi-GPU runs: every rank predicts its slab of the same domain (models.jl:236-247 chunking)."""
+    multi-GPU runs: every rank predicts its slab of the same domain (models.jl:236-247 chunking).
+    ``out`` may hold preallocated (pinned) arrays ``mean`` / ``var`` / ``status`` the results DMA into."""
     if not point:
         raise NotImplementedError("change of support (point=false) is not claimed by the GPU path")
     if distance != "euclidean":
@@ -413,7 +414,11 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
     alpha = _scale_factor(model, data.domain, dom)     # _scale, models.jl:118
     ctx = ctx or default_context(device)
-    ctx.set_samples(X * alpha, z)
+    sx, sz = _stage(ctx, X.shape[0], X.shape[1])
+    np.multiply(X, alpha, out=sx)                      # dat |> Scale(alpha), models.jl:279, into pinned memory
+    np.copyto(sz, z)
+    ctx.set_samples(sx, sz)
+    out = out or {}
     t = _targets_for(dom, alpha, first, count)
     radius = 0.0
     if neighborhood is not None:
@@ -432,7 +437,8 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         sm = model._scaled(alpha)
         if neighbors:
             mean, var, st, _ = ctx.local_krige(sm.fun._c(), sm._c(), t, _clamp_max(maxneighbors, len(z)),
-                                               minneighbors, radius, want_var=prob)
+                                               minneighbors, radius, want_var=prob, out_mean=out.get("mean"),
+                                               out_var=out.get("var"), out_status=out.get("status"))
         else:
             gfit = ctx.global_fit(sm.fun._c(), sm._c())
             mean, var = gfit.predict(t, want_var=prob)
@@ -450,6 +456,15 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     pred.domain = out_dom if out_dom is not None else dom   # georef over the ORIGINAL domain, models.jl:128
     pred.shard = (first, M)
     return pred
+
+
+def _stage(ctx, n, dim):
+    """Page-locked staging for the scaled sample coordinates / values so the upload is one async DMA."""
+    st = getattr(ctx, "_stage_bufs", None)
+    if st is None or st[0].shape != (n, dim):
+        st = (_lib.PinnedArray((n, dim), np.float64), _lib.PinnedArray((n,), np.float64))
+        ctx._stage_bufs = st
+    return st[0].array, st[1].array
 
 
 def _clamp_max(maxneighbors, nobs):

@@ -290,7 +290,7 @@ def knn(X: np.ndarray, t: np.ndarray, k: int, radius: float | None = None):
     d2 = sqdist_keys(X, t)
     order = np.lexsort((np.arange(X.shape[0]), d2))[:k]
     if radius is not None:
-        order = order[d2[order] <= radius * radius]
+        order = order[np.sqrt(d2[order]) <= radius]  # dists .<= radius on IEEE sqrt distances
     return order.astype(np.int64)
 
 
