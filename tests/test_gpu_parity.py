@@ -264,3 +264,80 @@ def test_error_codes(gsm):
                       gsm.Context.point_targets(np.zeros((1, 3))), 8)
     assert e.value.code == L.GSM_ERR_INVALID
     c.close()
+
+
+# ------------------------------------------------------------------------------- global Kriging
+GLOBAL_CASES = [("ok", 1, 2, None, 700), ("sk", 1, 2, None, 300), ("uk", 1, 2, 1, 500), ("uk", 2, 3, 2, 400),
+                ("ok", 2, 3, None, 129), ("ok", 1, 1, None, 64)]
+
+
+@pytest.mark.parametrize("kind,vk,dim,deg,n", GLOBAL_CASES)
+def test_global_kriging_matches_oracle(gsm, oracle, kind, vk, dim, deg, n):
+    o = oracle
+    X, z = _samples(200 + vk + dim, n, dim, 100.0)
+    vario = o.Variogram(vk, 1.0, 0.1, 30.0)
+    om = _oracle_model(o, kind, vario, dim, mean=float(z.mean()), deg=deg)
+    gm = _gsm_model(gsm, kind, vario, dim, mean=float(z.mean()), deg=deg)
+    dims = {1: (150,), 2: (13, 11), 3: (6, 5, 5)}[dim]
+    sp = tuple(100.0 / d for d in dims)
+    mu, var, st = o.fitpredict(om, X, z, o.Grid(tuple(0.0 for _ in dims), sp, dims), neighbors=False, prob=True)
+    grid = gsm.CartesianGrid(tuple(0.0 for _ in dims), tuple(100.0 for _ in dims), dims=dims)
+    got = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), grid, neighbors=False, prob=True).z
+    assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL), np.abs(got.mu - mu).max()
+    assert np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL), np.abs(got.sigma - var).max()
+
+
+def test_global_kriging_golden_misc_jl(gsm):
+    """reference test/misc.jl:13-21 (neighbors=false) through fit-once / predict-all on the GPU."""
+    data = gsm.georef({"z": np.array([1.0, 0.0, 1.0])}, [(25.0, 25.0), (50.0, 75.0), (75.0, 50.0)])
+    grid = gsm.CartesianGrid((0.5, 0.5), (100.5, 100.5), dims=(100, 100))
+    pred = gsm.fitpredict(gsm.Kriging(gsm.SphericalVariogram(range=35.0)), data, grid, neighbors=False)
+    lin = lambda i, j: (i - 1) + (j - 1) * 100
+    assert pred.z[lin(25, 25)] == pytest.approx(1.0, abs=1e-3)
+    assert pred.z[lin(50, 75)] == pytest.approx(0.0, abs=1e-3)
+    assert pred.z[lin(75, 50)] == pytest.approx(1.0, abs=1e-3)
+
+
+def test_fit_predict_predictprob_status_api(gsm):
+    """The single-target API of reference test/krig.jl:431-479 (fit / predict / predictprob / status)."""
+    pset = gsm.PointSet([(25.0, 25.0), (50.0, 75.0), (75.0, 50.0)])
+    data = gsm.georef({"a": np.array([1.0, 0.0, 0.0])}, pset)
+    p = (50.0, 50.0)
+    fm = gsm.fit(gsm.Kriging(gsm.SphericalVariogram(), 5.0), data)
+    assert gsm.predict(fm, "a", p) == pytest.approx(5.0, rel=1e-14)
+    assert gsm.status(fm)
+    fm = gsm.fit(gsm.Kriging(gsm.SphericalVariogram()), data)
+    assert gsm.predict(fm, "a", p) == pytest.approx(1 / 3, rel=1e-14)
+    assert gsm.predict(fm, ("a",), p) == [gsm.predict(fm, "a", p)]
+    d = gsm.predictprob(fm, "a", p)
+    assert isinstance(d, gsm.Normal) and d.mu == pytest.approx(1 / 3) and d.sigma == pytest.approx(np.sqrt(4 / 3 + 1e-10))
+    with pytest.raises(ValueError):
+        gsm.predict(fm, ("a", "b"), p)   # ArgumentError, models.jl:56-57
+    fm = gsm.fit(gsm.Kriging(gsm.SphericalVariogram(), [(0, 0), (1, 0), (0, 1)]), data)
+    assert gsm.predict(fm, "a", p) == pytest.approx(1 / 3, rel=1e-12)
+    fm = gsm.fit(gsm.Kriging(gsm.SphericalVariogram(), [(0, 0), (2, 0)]), data)
+    assert gsm.predict(fm, "a", p) == pytest.approx(0.4081632653061225, rel=1e-12)
+    with pytest.raises(ValueError):   # checkcompat, krig.jl:78-85
+        gsm.fit(gsm.Kriging(gsm.SphericalVariogram()), gsm.georef({"a": np.zeros(3), "b": np.zeros(3)}, pset))
+    # interpolation property at the samples (krig.jl:29-47) for a Gaussian variogram
+    rng = np.random.default_rng(2024)
+    P = rng.uniform(0, 10, size=(10, 3))
+    zz = rng.uniform(size=10)
+    tab = gsm.georef({"z": zz}, gsm.PointSet(P))
+    for model in (gsm.SimpleKriging(gsm.GaussianVariogram(), float(zz.mean())), gsm.OrdinaryKriging(gsm.GaussianVariogram()),
+                  gsm.UniversalKriging(gsm.GaussianVariogram(), 1, 3)):
+        fm = gsm.fit(model, tab)
+        for j in range(10):
+            d = gsm.predictprob(fm, "z", P[j])
+            assert d.mu == pytest.approx(zz[j], abs=1e-5) and d.sigma >= 0
+    # IDW fitted model (test/idw.jl:26-43)
+    fi = gsm.fit(gsm.IDW(), gsm.georef({"z": np.array([1.0, 0.0, 1.0])}, [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0)]))
+    assert gsm.predict(fi, "z", (0.0, 0.0)) == 1.0 and gsm.status(fi)
+
+
+def test_global_kriging_singular_status(gsm):
+    """Duplicate samples with zero nugget: the factorisation fails and status(fitted) is false
+    (krig.jl:49-52, check=false at krig.jl:152)."""
+    P = np.array([[0.0, 0.0], [1.0, 1.0], [1.0, 1.0], [2.0, 0.5]])
+    fm = gsm.fit(gsm.OrdinaryKriging(gsm.SphericalVariogram(range=5.0)), gsm.georef({"z": np.arange(4.0)}, gsm.PointSet(P)))
+    assert not gsm.status(fm)
