@@ -193,22 +193,22 @@ def run_ours(args):
 
     # ---- samples: generated on rank 0, replicated with one NCCL broadcast --------------------------
     alpha = 1.0 / max(VARIO["range"], float(NX), float(NY * world))    # _scale, models.jl:272-284
-    packed = torch.empty((n, 3), dtype=torch.float64, device=dev)       # x, y, z per sample
+    Xs = zs = None
     if rank == 0:
         X, z = make_samples(world)
         assert alpha == 1.0 / max(VARIO["range"], np.abs(X).max(), float(max(NX, NY * world)))
-        packed.copy_(torch.from_numpy(np.concatenate([X * alpha, z[:, None]], axis=1)))
-    bcast_ms = 0.0
+        Xs, zs = X * alpha, z
     if world > 1:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(packed, src=0)
-        e1.record()
-        torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-    coords_d = packed[:, :2].contiguous()
-    values_d = packed[:, 2].contiguous()
+        dist.barrier()            # communicator set-up is not part of the broadcast time
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    coords_d, values_d = gsm.distributed.replicate_samples(Xs, zs, src=0, device=dev)
+    e1.record()
+    torch.cuda.synchronize()
+    bcast_ms = e0.elapsed_time(e1) if world > 1 else 0.0
+    first, count = gsm.distributed.shard(M * world, rank, world)
+    assert (first, count) == (rank * M, M)
 
     vario = L.make_variogram(L.GSM_VARIO_SPHERICAL, VARIO["sill"], VARIO["nugget"], alpha * VARIO["range"])
     model = L.make_model(L.GSM_KRIG_ORDINARY)
@@ -255,8 +255,8 @@ def run_ours(args):
     # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region -------------------
     Xh = gsm.PinnedArray((n, 2), np.float64)
     zh = gsm.PinnedArray((n,), np.float64)
-    Xh.array[:] = (packed[:, :2] / alpha).cpu().numpy()
-    zh.array[:] = packed[:, 2].cpu().numpy()
+    Xh.array[:] = (coords_d / alpha).cpu().numpy()
+    zh.array[:] = values_d.cpu().numpy()
     pm, pv, ps = gsm.PinnedArray((M,), np.float64), gsm.PinnedArray((M,), np.float64), gsm.PinnedArray((M,), np.uint8)
     table = gsm.georef({"z": zh.array}, gsm.PointSet(Xh.array))   # contiguous float64: wrapped, not copied
     grid = gsm.CartesianGrid(NX, NY * world)

@@ -7,3 +7,4 @@ from . import _lib
 from .api import *  # noqa: F401,F403
 from .api import monomial_exponents  # noqa: F401
 from ._lib import Context, GsmError, PinnedArray  # noqa: F401
+from . import distributed  # noqa: F401,E402
