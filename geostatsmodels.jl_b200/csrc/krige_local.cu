@@ -13,6 +13,8 @@
 //   Drift monomials are evaluated on coordinates centred at the target and scaled by the neighbourhood
 //   radius when the exponent set is a lower set (then the spanned polynomial space, hence the
 //   prediction, is unchanged while G stays well conditioned); otherwise on the raw coordinates.
+#include <cstdlib>
+
 #include "gsm_internal.cuh"
 
 namespace {
@@ -253,7 +255,15 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   } else if (m.kind == GSM_KRIG_UNIVERSAL) {
     ncon = m.ndrift;
   }
-  const int centered = (ncon > 0 && is_lower_set(m)) ? 1 : 0;
+  bool nonconst = false;
+  for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
+  const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
+  static const bool force_v1 = getenv("GSM_LOCAL_V1") != nullptr;   // A/B switch for profiling
+  if (!force_v1) {
+    int rc = gsm_launch_local_krige_dmma(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
+                                         d_status);
+    if (rc != GSM_ERR_UNSUPPORTED) return rc;
+  }
 #define GSM_LK_CASE(N) \
   case N:              \
     return launch<N>(ctx, v, m, tg, k, minneighbors, centered, d_pos, d_cnt, d_mean, d_var, d_status);
