@@ -31,6 +31,20 @@ __device__ __forceinline__ void dmma(double2& d, double a, double b) {
                : "d"(a), "d"(b));
 }
 
+// Named barriers (ids 1, 2) for the post / wait hand-off between system warps and the diagonal warp:
+// the poster arrives without waiting, the consumer syncs.
+constexpr int BAR_READY = 1, BAR_DONE = 2;
+__device__ __forceinline__ void bar_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(STHREADS) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(STHREADS) : "memory");
+}
+__device__ __forceinline__ void bar_sync_sys(int id) {   // the SW system warps only
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(SW * 32) : "memory");
+}
+
 // 1/sqrt(d), d > 0: hardware seed (rel. error ~2^-22) + one third-order step -> full double precision
 __device__ __forceinline__ double fast_rsqrt(double d) {
   double y;
@@ -130,6 +144,28 @@ struct SysSmem {
   double rhs[8][32];
 };
 
+// Covariance pool shared by the SW systems of a group: consecutive targets share most neighbours, so
+// the pairwise covariances are evaluated once per distinct sample pair of the group and every system
+// gathers its 32x32 block from the pooled matrix (bit-identical values: cov is a function of the pair).
+constexpr int PMAX = 64;          // pool capacity (distinct samples per group); larger unions fall back
+constexpr int PLD = PMAX + 1;     // leading dimension of the pooled matrix (odd: spreads banks)
+constexpr int HSIZE = 512;        // open-addressing table for de-duplicating neighbour positions
+constexpr int BAR_POOL = 3;       // named barrier among the system warps only
+constexpr int SYS_THREADS = SW * 32;
+
+struct KernelSmem {
+  double exin[SW * EXS];
+  double exout[SW * EXS];
+  SysSmem sys[SW];
+  double PC[PMAX * PLD];
+  double ppx[PMAX], ppy[PMAX], ppz[PMAX];
+  int hkey[HSIZE];
+  int hid[HSIZE];
+  int ids[SW][32];
+  int flag[SW];
+  int pcount;
+};
+
 template <int NCON, bool DIM3>
 __global__ void __launch_bounds__(STHREADS, 2)
 local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int minn, int centered,
@@ -137,10 +173,12 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
                         double* __restrict__ out_var, unsigned char* __restrict__ out_status) {
   constexpr int NR = 2 + NCON;
   static_assert(NR <= 8, "at most 8 right-hand-side rows");
-  __shared__ __align__(16) double s_exin[SW * EXS];
-  __shared__ __align__(16) double s_exout[SW * EXS];
-  __shared__ __align__(16) SysSmem s_sys[SW];
-  __shared__ int s_flag[SW];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KernelSmem& S = *reinterpret_cast<KernelSmem*>(smem_raw);
+  double* s_exin = S.exin;
+  double* s_exout = S.exout;
+  SysSmem* s_sys = S.sys;
+  int* s_flag = S.flag;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -149,6 +187,8 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   for (int e = threadIdx.x; e < SW * EXS; e += STHREADS) s_exout[e] = 0.0;
+  for (int e = threadIdx.x; e < HSIZE; e += STHREADS) S.hkey[e] = -1;
+  if (threadIdx.x == 0) S.pcount = 0;
   __syncthreads();
 
   if (warp == SW) {
@@ -156,11 +196,11 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb) {
-        __syncthreads();
+        bar_sync(BAR_READY);
         if (lane < SW) {
           if (diag_block(&s_exin[lane * EXS], &s_exout[lane * EXS])) s_flag[lane] = 1;
         }
-        __syncthreads();
+        bar_arrive(BAR_DONE);
       }
     }
     return;
@@ -181,7 +221,11 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     // ---- gather neighbours, right-hand-side rows -------------------------------------------
     const bool live = lane < n;
     double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (live) r = b.rec[pos[tt * (long long)k + lane]];
+    int mypos = -1;
+    if (live) {
+      mypos = pos[tt * (long long)k + lane];
+      r = b.rec[mypos];
+    }
     sm.px[lane] = r.x;
     sm.py[lane] = r.y;
     if (DIM3) sm.pz[lane] = r.z;
@@ -207,31 +251,95 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       }
     }
     if (lane == 0) s_flag[warp] = 0;
-    __syncwarp();
+
+    // ---- pool the distinct neighbours of the group and their pairwise covariances ------------
+    int myslot = 0;
+    bool owner = false;
+    if (live) {
+      myslot = (int)(((unsigned)mypos * 0x9E3779B1u) >> 23);
+      for (;;) {
+        const int old = atomicCAS(&S.hkey[myslot], -1, mypos);
+        if (old == -1) {
+          owner = true;
+          break;
+        }
+        if (old == mypos) break;
+        myslot = (myslot + 1) & (HSIZE - 1);
+      }
+    }
+    bar_sync_sys(BAR_POOL);
+    if (owner) {
+      const int id = atomicAdd(&S.pcount, 1);
+      S.hid[myslot] = id;
+      if (id < PMAX) {
+        S.ppx[id] = r.x;
+        S.ppy[id] = r.y;
+        S.ppz[id] = r.z;
+      }
+    }
+    bar_sync_sys(BAR_POOL);
+    const int P = S.pcount;
+    const bool pooled = P <= PMAX;
+    S.ids[warp][lane] = live ? S.hid[myslot] : -1;
+    if (pooled) {
+      const int npairs = P * (P + 1) / 2;
+      for (int e = warp * 32 + lane; e < npairs; e += SYS_THREADS) {
+        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while (a * (a + 1) / 2 > e) --a;
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        const int bcol = e - a * (a + 1) / 2;
+        double val = v.sill;
+        if (a != bcol) {
+          const double dx = S.ppx[a] - S.ppx[bcol], dy = S.ppy[a] - S.ppy[bcol];
+          const double dz = DIM3 ? S.ppz[a] - S.ppz[bcol] : 0.0;
+          val = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
+        }
+        S.PC[a * PLD + bcol] = val;
+        S.PC[bcol * PLD + a] = val;
+      }
+    }
+    bar_sync_sys(BAR_POOL);
+    // every lookup of this group is done: release the table for the next group
+    if (live) S.hkey[myslot] = -1;
+    if (warp == 0 && lane == 0) S.pcount = 0;
 
     // ---- assemble the augmented matrix in accumulator layout ---------------------------------
+    // Block (0,0) first: it is posted to the diagonal warp at once so its factorisation overlaps
+    // the assembly of the other 14 blocks.
     double2 A[5][5];
-#pragma unroll
-    for (int I = 0; I < 4; ++I) {
+    auto assemble = [&](int I, int J) {
+      if (pooled) {
+        const int row = 8 * I + g, col = 8 * J + 2 * t;
+        const int ir = S.ids[warp][row];
+        const int2 ic = *reinterpret_cast<const int2*>(&S.ids[warp][col]);
+        double c0 = (row == col) ? 1.0 : 0.0, c1 = (row == col + 1) ? 1.0 : 0.0;
+        if (ir >= 0 && ic.x >= 0) c0 = S.PC[ir * PLD + ic.x];
+        if (ir >= 0 && ic.y >= 0) c1 = S.PC[ir * PLD + ic.y];
+        return make_double2(c0, c1);
+      }
       const int row = 8 * I + g;
       const double xr = sm.px[row], yr = sm.py[row], zr = DIM3 ? sm.pz[row] : 0.0;
       const bool rowlive = row < n;
+      const int col = 8 * J + 2 * t;
+      const double2 xc = *reinterpret_cast<const double2*>(&sm.px[col]);
+      const double2 yc = *reinterpret_cast<const double2*>(&sm.py[col]);
+      double2 zc = make_double2(0.0, 0.0);
+      if (DIM3) zc = *reinterpret_cast<const double2*>(&sm.pz[col]);
+      double dx = xr - xc.x, dy = yr - yc.x, dz = zr - zc.x;
+      double c0 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
+      dx = xr - xc.y, dy = yr - yc.y, dz = zr - zc.y;
+      double c1 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
+      c0 = (row == col) ? (rowlive ? v.sill : 1.0) : ((rowlive && col < n) ? c0 : 0.0);
+      c1 = (row == col + 1) ? (rowlive ? v.sill : 1.0) : ((rowlive && col + 1 < n) ? c1 : 0.0);
+      return make_double2(c0, c1);
+    };
+    A[0][0] = assemble(0, 0);
+    *reinterpret_cast<double2*>(&s_exin[warp * EXS + g * 8 + 2 * t]) = A[0][0];
+    bar_arrive(BAR_READY);
 #pragma unroll
-      for (int J = 0; J <= I; ++J) {
-        const int col = 8 * J + 2 * t;
-        const double2 xc = *reinterpret_cast<const double2*>(&sm.px[col]);
-        const double2 yc = *reinterpret_cast<const double2*>(&sm.py[col]);
-        double2 zc = make_double2(0.0, 0.0);
-        if (DIM3) zc = *reinterpret_cast<const double2*>(&sm.pz[col]);
-        double dx = xr - xc.x, dy = yr - yc.x, dz = zr - zc.x;
-        double c0 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
-        dx = xr - xc.y, dy = yr - yc.y, dz = zr - zc.y;
-        double c1 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
-        c0 = (row == col) ? (rowlive ? v.sill : 1.0) : ((rowlive && col < n) ? c0 : 0.0);
-        c1 = (row == col + 1) ? (rowlive ? v.sill : 1.0) : ((rowlive && col + 1 < n) ? c1 : 0.0);
-        A[I][J] = make_double2(c0, c1);
-      }
-    }
+    for (int I = 1; I < 4; ++I)
+#pragma unroll
+      for (int J = 0; J <= I; ++J) A[I][J] = assemble(I, J);
 #pragma unroll
     for (int J = 0; J < 4; ++J) {
       double2 val = make_double2(0.0, 0.0);
@@ -241,28 +349,34 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     A[4][4] = make_double2(0.0, 0.0);
 
     // ---- blocked Cholesky with the RHS rows riding along ------------------------------------
+    // Look-ahead: at step kb the next diagonal block (kb+1,kb+1) is finished and posted first, the
+    // rest of the trailing update runs while the diagonal warp factors it.
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
-      *reinterpret_cast<double2*>(&s_exin[warp * EXS + g * 8 + 2 * t]) = A[kb][kb];
-      __syncthreads();
-      __syncthreads();
+      bar_sync(BAR_DONE);
       const double2 W = *reinterpret_cast<const double2*>(&s_exout[warp * EXS + g * 8 + 2 * t]);
-#pragma unroll
-      for (int i = kb + 1; i < 5; ++i) {   // panel: L_ik = A_ik W'
+      auto panel = [&](int i) {   // L_ik = A_ik W'
         double2 acc = make_double2(0.0, 0.0);
         dmma(acc, A[i][kb].x, W.x);
         dmma(acc, A[i][kb].y, W.y);
         A[i][kb] = acc;
+      };
+      auto update = [&](int i, int j) {   // A_ij -= L_ik L_jk'
+        dmma(A[i][j], -A[i][kb].x, A[j][kb].x);
+        dmma(A[i][j], -A[i][kb].y, A[j][kb].y);
+      };
+      panel(kb + 1);
+      update(kb + 1, kb + 1);
+      if (kb < 3) {
+        *reinterpret_cast<double2*>(&s_exin[warp * EXS + g * 8 + 2 * t]) = A[kb + 1][kb + 1];
+        bar_arrive(BAR_READY);
       }
 #pragma unroll
-      for (int i = kb + 1; i < 5; ++i) {   // trailing update: A_ij -= L_ik L_jk'
-        const double nx = -A[i][kb].x, ny = -A[i][kb].y;
+      for (int i = kb + 2; i < 5; ++i) panel(i);
 #pragma unroll
-        for (int j = kb + 1; j <= i; ++j) {
-          dmma(A[i][j], nx, A[j][kb].x);
-          dmma(A[i][j], ny, A[j][kb].y);
-        }
-      }
+      for (int i = kb + 2; i < 5; ++i)
+#pragma unroll
+        for (int j = kb + 1; j <= i; ++j) update(i, j);
     }
 
     // ---- epilogue: the trailing block is -B'C^-1B ---------------------------------------------
@@ -354,12 +468,16 @@ int launch_dmma(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const Target
                 int centered, const int* pos, const int* cnt, double* mean, double* var, unsigned char* status) {
   const long long ngroups = (tg.count + SW - 1) / SW;
   const int blocks = (int)std::min<long long>(ngroups, 148LL * 2);
-  if (ctx->dim >= 3)
-    local_krige_dmma_kernel<NCON, true><<<blocks, STHREADS, 0, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
-                                                                             pos, cnt, mean, var, status);
-  else
-    local_krige_dmma_kernel<NCON, false><<<blocks, STHREADS, 0, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
-                                                                              pos, cnt, mean, var, status);
+  const size_t smem = sizeof(KernelSmem);
+  if (ctx->dim >= 3) {
+    GSM_CUDA(ctx, cudaFuncSetAttribute(local_krige_dmma_kernel<NCON, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    local_krige_dmma_kernel<NCON, true><<<blocks, STHREADS, smem, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
+                                                                                pos, cnt, mean, var, status);
+  } else {
+    GSM_CUDA(ctx, cudaFuncSetAttribute(local_krige_dmma_kernel<NCON, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    local_krige_dmma_kernel<NCON, false><<<blocks, STHREADS, smem, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
+                                                                                 pos, cnt, mean, var, status);
+  }
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
   return GSM_OK;
