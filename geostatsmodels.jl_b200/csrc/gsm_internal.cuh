@@ -153,10 +153,26 @@ int gsm_fp64_peak(gsm_ctx* ctx, double* dfma, double* dmma);
 __device__ __forceinline__ void gsm_target_coords(const TargetsDev& tg, long long lin, double& x, double& y,
                                                   double& z) {
   if (tg.kind == GSM_TARGETS_GRID) {
-    long long i0 = lin % tg.dims[0];
-    long long r = lin / tg.dims[0];
-    long long i1 = r % tg.dims[1];
-    long long i2 = r / tg.dims[1];
+    long long i0, i1, i2;
+    if ((unsigned long long)lin < 0x80000000ULL && tg.dims[0] < 0x80000000LL && tg.dims[1] < 0x80000000LL) {
+      // 32-bit index arithmetic (the common case; 64-bit division costs hundreds of instructions)
+      const unsigned l = (unsigned)lin, d0 = (unsigned)tg.dims[0], d1 = (unsigned)tg.dims[1];
+      const unsigned r = l / d0;
+      i0 = l - r * d0;
+      if (tg.dim > 2) {
+        const unsigned q = r / d1;
+        i1 = r - q * d1;
+        i2 = q;
+      } else {
+        i1 = r;
+        i2 = 0;
+      }
+    } else {
+      i0 = lin % tg.dims[0];
+      const long long r = lin / tg.dims[0];
+      i1 = r % tg.dims[1];
+      i2 = r / tg.dims[1];
+    }
     x = __dadd_rn(__dadd_rn(tg.origin[0], __dmul_rn((double)i0, tg.spacing[0])), __dmul_rn(tg.spacing[0], 0.5));
     y = __dadd_rn(__dadd_rn(tg.origin[1], __dmul_rn((double)i1, tg.spacing[1])), __dmul_rn(tg.spacing[1], 0.5));
     z = __dadd_rn(__dadd_rn(tg.origin[2], __dmul_rn((double)i2, tg.spacing[2])), __dmul_rn(tg.spacing[2], 0.5));

@@ -19,6 +19,21 @@
 
 #include "gsm_internal.cuh"
 
+#ifdef GSM_TRACE
+// Developer-only phase trace (make trace): clock64 stamps of CTA 0 for a few group iterations.
+__device__ long long* g_trace = nullptr;
+extern "C" __attribute__((visibility("default"))) int gsm_debug_set_trace(long long* p) {
+  return cudaMemcpyToSymbol(g_trace, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
+}
+#define TR(slot)                                                                                      \
+  do {                                                                                                \
+    if (g_trace && blockIdx.x == 0 && lane == 0 && grp >= 20LL * gridDim.x && grp < 24LL * gridDim.x) \
+      g_trace[(((grp / gridDim.x) - 20) * 9 + warp) * 40 + (slot)] = clock64();                       \
+  } while (0)
+#else
+#define TR(slot) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int SW = 8;                      // system warps per CTA
@@ -188,6 +203,7 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
 
   for (int e = threadIdx.x; e < SW * EXS; e += STHREADS) s_exout[e] = 0.0;
   for (int e = threadIdx.x; e < HSIZE; e += STHREADS) S.hkey[e] = -1;
+  for (int e = threadIdx.x; e < PMAX; e += STHREADS) S.ppx[e] = S.ppy[e] = S.ppz[e] = 0.0;
   if (threadIdx.x == 0) S.pcount = 0;
   __syncthreads();
 
@@ -196,11 +212,14 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb) {
+        TR(kb * 3 + 0);
         bar_sync(BAR_READY);
+        TR(kb * 3 + 1);
         if (lane < SW) {
           if (diag_block(&s_exin[lane * EXS], &s_exout[lane * EXS])) s_flag[lane] = 1;
         }
         bar_arrive(BAR_DONE);
+        TR(kb * 3 + 2);
       }
     }
     return;
@@ -210,6 +229,7 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
   const CovFast cf = make_cov(v);
   SysSmem& sm = s_sys[warp];
   for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    TR(0);
     const long long tt = grp * SW + warp;
     const bool valid = tt < tg.count;
     int n = valid ? cnt[tt] : 0;
@@ -251,6 +271,7 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       }
     }
     if (lane == 0) s_flag[warp] = 0;
+    TR(1);
 
     // ---- pool the distinct neighbours of the group and their pairwise covariances ------------
     int myslot = 0;
@@ -268,6 +289,7 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       }
     }
     bar_sync_sys(BAR_POOL);
+    TR(2);
     if (owner) {
       const int id = atomicAdd(&S.pcount, 1);
       S.hid[myslot] = id;
@@ -278,16 +300,20 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       }
     }
     bar_sync_sys(BAR_POOL);
+    TR(3);
     const int P = S.pcount;
     const bool pooled = P <= PMAX;
     S.ids[warp][lane] = live ? S.hid[myslot] : -1;
     if (pooled) {
-      const int npairs = P * (P + 1) / 2;
+      // lower triangle (with diagonal) of the P x P pooled matrix, folded into a (Pe/2) x (Pe+1) rectangle
+      // (Pe = P rounded up to even; a dummy last entry is computed and never read)
+      const int Pe = P + (P & 1), Wd = Pe + 1, npairs = (Pe >> 1) * Wd;
+      const float invW = 1.0f / (float)Wd;
       for (int e = warp * 32 + lane; e < npairs; e += SYS_THREADS) {
-        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while (a * (a + 1) / 2 > e) --a;
-        while ((a + 1) * (a + 2) / 2 <= e) ++a;
-        const int bcol = e - a * (a + 1) / 2;
+        const int rr = (int)(((float)e + 0.5f) * invW);
+        const int cc = e - rr * Wd;
+        const int a = (cc <= rr) ? rr : Pe - 1 - rr;
+        const int bcol = (cc <= rr) ? cc : cc - rr - 1;
         double val = v.sill;
         if (a != bcol) {
           const double dx = S.ppx[a] - S.ppx[bcol], dy = S.ppy[a] - S.ppy[bcol];
@@ -298,7 +324,9 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
         S.PC[bcol * PLD + a] = val;
       }
     }
+    TR(4);
     bar_sync_sys(BAR_POOL);
+    TR(5);
     // every lookup of this group is done: release the table for the next group
     if (live) S.hkey[myslot] = -1;
     if (warp == 0 && lane == 0) S.pcount = 0;
@@ -336,6 +364,7 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     A[0][0] = assemble(0, 0);
     *reinterpret_cast<double2*>(&s_exin[warp * EXS + g * 8 + 2 * t]) = A[0][0];
     bar_arrive(BAR_READY);
+    TR(6);
 #pragma unroll
     for (int I = 1; I < 4; ++I)
 #pragma unroll
@@ -347,36 +376,58 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       A[4][J] = val;
     }
     A[4][4] = make_double2(0.0, 0.0);
+    TR(7);
 
     // ---- blocked Cholesky with the RHS rows riding along ------------------------------------
     // Look-ahead: at step kb the next diagonal block (kb+1,kb+1) is finished and posted first, the
     // rest of the trailing update runs while the diagonal warp factors it.
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
+      TR(8 + kb * 4);
       bar_sync(BAR_DONE);
+      TR(9 + kb * 4);
       const double2 W = *reinterpret_cast<const double2*>(&s_exout[warp * EXS + g * 8 + 2 * t]);
-      auto panel = [&](int i) {   // L_ik = A_ik W'
-        double2 acc = make_double2(0.0, 0.0);
-        dmma(acc, A[i][kb].x, W.x);
-        dmma(acc, A[i][kb].y, W.y);
-        A[i][kb] = acc;
-      };
-      auto update = [&](int i, int j) {   // A_ij -= L_ik L_jk'
-        dmma(A[i][j], -A[i][kb].x, A[j][kb].x);
-        dmma(A[i][j], -A[i][kb].y, A[j][kb].y);
-      };
-      panel(kb + 1);
-      update(kb + 1, kb + 1);
+      // Each product is two k-chunks (accumulator slots x and y).  All x-chunks are issued before the
+      // y-chunks so consecutive DMMAs never wait on each other's accumulator.
+      {   // first the row that produces the next diagonal block
+        double2 acc = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
+        dmma(acc, A[kb + 1][kb].x, W.x);
+        dmma(acc2, A[kb + 1][kb].y, W.y);
+        A[kb + 1][kb] = make_double2(acc.x + acc2.x, acc.y + acc2.y);   // L_{kb+1,kb} = A_{kb+1,kb} W'
+        double2 u = make_double2(0.0, 0.0);
+        dmma(A[kb + 1][kb + 1], -A[kb + 1][kb].x, A[kb + 1][kb].x);
+        dmma(u, -A[kb + 1][kb].y, A[kb + 1][kb].y);
+        A[kb + 1][kb + 1].x += u.x;
+        A[kb + 1][kb + 1].y += u.y;
+      }
       if (kb < 3) {
         *reinterpret_cast<double2*>(&s_exin[warp * EXS + g * 8 + 2 * t]) = A[kb + 1][kb + 1];
         bar_arrive(BAR_READY);
       }
+      TR(10 + kb * 4);
+      {   // remaining panel rows: L_ik = A_ik W'
+        double2 acc[5];
 #pragma unroll
-      for (int i = kb + 2; i < 5; ++i) panel(i);
+        for (int i = kb + 2; i < 5; ++i) {
+          acc[i] = make_double2(0.0, 0.0);
+          dmma(acc[i], A[i][kb].x, W.x);
+        }
+#pragma unroll
+        for (int i = kb + 2; i < 5; ++i) {
+          dmma(acc[i], A[i][kb].y, W.y);
+          A[i][kb] = acc[i];
+        }
+      }
+      // remaining trailing update: A_ij -= L_ik L_jk'
 #pragma unroll
       for (int i = kb + 2; i < 5; ++i)
 #pragma unroll
-        for (int j = kb + 1; j <= i; ++j) update(i, j);
+        for (int j = kb + 1; j <= i; ++j) dmma(A[i][j], -A[i][kb].x, A[j][kb].x);
+#pragma unroll
+      for (int i = kb + 2; i < 5; ++i)
+#pragma unroll
+        for (int j = kb + 1; j <= i; ++j) dmma(A[i][j], -A[i][kb].y, A[j][kb].y);
+      TR(11 + kb * 4);
     }
 
     // ---- epilogue: the trailing block is -B'C^-1B ---------------------------------------------
@@ -460,6 +511,7 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       }
     }
     __syncwarp();
+    TR(24);
   }
 }
 
