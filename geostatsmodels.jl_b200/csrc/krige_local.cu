@@ -258,8 +258,15 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool nonconst = false;
   for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
   const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
-  static const bool force_v1 = getenv("GSM_LOCAL_V1") != nullptr;   // A/B switch for profiling
-  if (!force_v1) {
+  // implementation switch for A/B profiling: GSM_LOCAL_IMPL = pipe (default) | dmma | v1
+  static const char* impl_env = getenv("GSM_LOCAL_IMPL");
+  const std::string impl = impl_env ? impl_env : "pipe";
+  if (impl == "pipe") {
+    int rc = gsm_launch_local_krige_pipe(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
+                                         d_status);
+    if (rc != GSM_ERR_UNSUPPORTED) return rc;
+  }
+  if (impl == "dmma") {
     int rc = gsm_launch_local_krige_dmma(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                          d_status);
     if (rc != GSM_ERR_UNSUPPORTED) return rc;
