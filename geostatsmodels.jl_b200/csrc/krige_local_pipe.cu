@@ -9,19 +9,34 @@
 //   * The whole pre-phase of the NEXT group (neighbour loads, covariance to the target, right-hand-side
 //     rows, hash de-duplication, pooled pair covariances) is issued inside the four wait slots of the
 //     CURRENT group's factorisation, so its global-load and barrier latencies are hidden.
-//   * Pool of up to 96 distinct samples per group, packed lower-triangular (37 KB), single-buffered:
+//   * Pool of up to 72 distinct samples per group (full 72 x 73 matrix, 42 KB), single-buffered:
 //     every gather of the current group precedes the slot in which the next pool is evaluated.
 #include <algorithm>
 
 #include "gsm_internal.cuh"
+
+#ifdef GSM_TRACE
+__device__ long long* g_trace2 = nullptr;
+extern "C" __attribute__((visibility("default"))) int gsm_debug_set_trace2(long long* p) {
+  return cudaMemcpyToSymbol(g_trace2, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
+}
+#define TR(slot)                                                                                       \
+  do {                                                                                                 \
+    if (g_trace2 && blockIdx.x == 0 && lane == 0 && grp >= 20LL * gridDim.x && grp < 24LL * gridDim.x) \
+      g_trace2[(((grp / gridDim.x) - 20) * 9 + warp) * 40 + (slot)] = clock64();                       \
+  } while (0)
+#else
+#define TR(slot) do {} while (0)
+#endif
 
 namespace {
 
 constexpr int SW = 8;                      // system warps per CTA
 constexpr int NTH = (SW + 1) * 32;         // + 1 diagonal-block warp
 constexpr int EXS = 66;                    // padded stride (doubles) of one exchanged 8x8 block
-constexpr int PMAX = 96;                   // pool capacity (distinct samples per group)
-constexpr int PTRI = PMAX * (PMAX + 1) / 2;
+constexpr int PMAX = 72;                   // pool capacity (distinct samples per group)
+constexpr int PLD = PMAX + 1;              // leading dimension of the pooled matrix (odd: spreads banks)
+constexpr int BAR_EPI = 4;                 // system warps -> diagonal warp: Schur block ready for the epilogue
 constexpr int HSIZE = 512;                 // open-addressing table for de-duplicating positions
 constexpr int BAR_READY = 1, BAR_DONE = 2, BAR_POOL = 3;
 
@@ -35,6 +50,7 @@ __device__ __forceinline__ void bar_arrive(int id) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTH) : "memory");
 }
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTH) : "memory"); }
+__device__ __forceinline__ void bar_sync_sys_all() { asm volatile("bar.sync %0, %1;" ::"n"(5), "n"(NTH) : "memory"); }
 __device__ __forceinline__ void bar_sync_sys() {
   asm volatile("bar.sync %0, %1;" ::"n"(BAR_POOL), "n"(SW * 32) : "memory");
 }
@@ -134,7 +150,11 @@ struct alignas(16) PipeSmem {
   double exout[SW * EXS];
   double px[2][SW][32], py[2][SW][32], pz[2][SW][32];   // neighbour coordinates (direct-assembly fallback)
   double rhs[2][SW][NR][32];                            // right-hand-side rows: c0, z, drifts
-  double PC[PTRI];                                      // pooled covariances, packed lower triangle
+  double PC[PMAX * PLD];                                // pooled covariances, full symmetric
+  double Gx[SW * EXS];                                  // trailing Schur blocks handed to the epilogue
+  double tgt[2][SW][4];                                 // target coordinates of the groups in flight
+  long long e_tt[SW];                                   // epilogue hand-off: target index, flags
+  int e_flags[SW];
   double ppx[PMAX], ppy[PMAX], ppz[PMAX];
   int hkey[HSIZE];
   int hid[HSIZE];
@@ -166,15 +186,114 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
   __syncthreads();
 
   if (warp == SW) {
-    // ---------------- diagonal-block warp: one block per lane ----------------
-    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    // ---------------- diagonal-block warp: one lane per system ----------------
+    // Besides the four diagonal blocks it does the per-system scalar work thread-per-system: target
+    // coordinates of the next group and the Schur-complement epilogue (mean, variance, status).
+    auto coords_for = [&](long long grp, int bf) {
+      if (lane < SW) {
+        const long long tt = grp * SW + lane;
+        double x = 0.0, y = 0.0, z = 0.0;
+        if (grp < ngroups && tt < tg.count) gsm_target_coords(tg, tg.first + tt, x, y, z);
+        S.tgt[bf][lane][0] = x;
+        S.tgt[bf][lane][1] = y;
+        S.tgt[bf][lane][2] = z;
+      }
+    };
+    int dbuf = 0;
+    coords_for(blockIdx.x, 0);
+    __threadfence_block();
+    bar_sync_sys_all();   // prologue hand-off of the first group's coordinates
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, dbuf ^= 1) {
+      coords_for(grp + gridDim.x, dbuf ^ 1);
+      if (lane < SW) S.flag[lane] = 0;
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb) {
+        TR(kb * 3 + 0);
         bar_sync(BAR_READY);
+        TR(kb * 3 + 1);
         if (lane < SW) {
           if (diag_block(&S.exin[lane * EXS], &S.exout[lane * EXS])) S.flag[lane] = 1;
         }
         bar_arrive(BAR_DONE);
+        TR(kb * 3 + 2);
+      }
+      bar_sync(BAR_EPI);
+      if (lane < SW && (S.e_flags[lane] & 1)) {
+        const double* Gm = &S.Gx[lane * EXS];   // Gm[a*8+b] = -G[a][b]
+        const long long tt = S.e_tt[lane];
+        bool singular = S.flag[lane] != 0;
+        const double uu = -Gm[0], wu = -Gm[8];
+        const double c0 = v.sill;
+        double mean, var;
+        if (NCON == 0) {
+          mean = m.mean + wu;
+          var = c0 - uu;
+        } else {
+          double Gs[NCON > 0 ? NCON * NCON : 1], gq[NCON > 0 ? NCON : 1], hw[NCON > 0 ? NCON : 1];
+#pragma unroll
+          for (int p = 0; p < NCON; ++p) {
+            gq[p] = -Gm[(2 + p) * 8 + 0];
+            hw[p] = -Gm[(2 + p) * 8 + 1];
+#pragma unroll
+            for (int q = 0; q <= p; ++q) Gs[p * NCON + q] = -Gm[(2 + p) * 8 + 2 + q];
+          }
+          if (centered) {
+#pragma unroll
+            for (int p = 0; p < NCON; ++p)
+              gq[p] -= (m.exps[p][0] == 0 && m.exps[p][1] == 0 && m.exps[p][2] == 0) ? 1.0 : 0.0;
+          } else {
+            const double tx = S.tgt[dbuf][lane][0], ty = S.tgt[dbuf][lane][1], tz = S.tgt[dbuf][lane][2];
+#pragma unroll
+            for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, tx, ty, tz);
+          }
+#pragma unroll
+          for (int j = 0; j < NCON; ++j) {
+            double d = Gs[j * NCON + j];
+            if (!(d > 0.0)) {
+              singular = true;
+              d = 1.0;
+            }
+            const double rs = rsqrt(d);
+            Gs[j * NCON + j] = rs;
+#pragma unroll
+            for (int i = j + 1; i < NCON; ++i) Gs[i * NCON + j] *= rs;
+#pragma unroll
+            for (int i = j + 1; i < NCON; ++i)
+#pragma unroll
+              for (int q = j + 1; q <= i; ++q)
+                Gs[i * NCON + q] = fma(-Gs[i * NCON + j], Gs[q * NCON + j], Gs[i * NCON + q]);
+          }
+          double y[NCON > 0 ? NCON : 1], hy[NCON > 0 ? NCON : 1];
+#pragma unroll
+          for (int i = 0; i < NCON; ++i) {
+            double s1 = gq[i], s2 = hw[i];
+#pragma unroll
+            for (int q = 0; q < i; ++q) {
+              s1 = fma(-Gs[i * NCON + q], y[q], s1);
+              s2 = fma(-Gs[i * NCON + q], hy[q], s2);
+            }
+            y[i] = s1 * Gs[i * NCON + i];
+            hy[i] = s2 * Gs[i * NCON + i];
+          }
+          double gnu = 0.0, hnu = 0.0;
+#pragma unroll
+          for (int i = 0; i < NCON; ++i) {
+            gnu = fma(y[i], y[i], gnu);
+            hnu = fma(hy[i], y[i], hnu);
+          }
+          mean = wu - hnu;
+          var = c0 - uu + gnu;
+        }
+        var += 1e-10;  // krig.jl:278-279
+        if (S.e_flags[lane] & 2) {
+          out_mean[tt] = qnan;
+          if (out_var) out_var[tt] = qnan;
+          if (out_status) out_status[tt] = GSM_ST_MISSING;
+        } else {
+          out_mean[tt] = singular ? qnan : mean;
+          if (out_var) out_var[tt] = singular ? qnan : var;
+          if (out_status) out_status[tt] = singular ? GSM_ST_SINGULAR : GSM_ST_OK;
+        }
       }
     }
     return;
@@ -204,7 +323,6 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     if (x_valid) {
       x_n = cnt[x_tt];
       if (lane < k) x_pos = pos[x_tt * (long long)k + lane];
-      gsm_target_coords(tg, tg.first + x_tt, x_tx, x_ty, x_tz);
     }
   };
   // P1: neighbour records
@@ -217,6 +335,9 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
   // P2+P3: coordinates / right-hand-side rows into buffer `bf`, hash insert, pool ids for owners
   auto P23 = [&](int bf) {
     const bool live = lane < x_n;
+    x_tx = S.tgt[bf][warp][0];   // written by the diagonal warp one phase ahead
+    x_ty = S.tgt[bf][warp][1];
+    x_tz = S.tgt[bf][warp][2];
     S.px[bf][warp][lane] = x_r.x;
     S.py[bf][warp][lane] = x_r.y;
     if (DIM3) S.pz[bf][warp][lane] = x_r.z;
@@ -282,7 +403,10 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
           const double dz = DIM3 ? S.ppz[a] - S.ppz[bc] : 0.0;
           val = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
         }
-        if (a < PMAX) S.PC[a * (a + 1) / 2 + bc] = val;
+        if (a < PMAX) {
+          S.PC[a * PLD + bc] = val;
+          S.PC[bc * PLD + a] = val;
+        }
       }
     }
   };
@@ -293,6 +417,7 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
   };
 
   // ---- prologue: prepare the first group --------------------------------------------------
+  bar_sync_sys_all();   // first group's target coordinates (diagonal warp)
   P0(blockIdx.x);
   P1();
   P23(0);
@@ -314,15 +439,16 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     c_tz = x_tz;
     const bool pooled = c_P <= PMAX;
     const int n = c_n;
-    if (lane == 0) S.flag[warp] = 0;
 
-    int irow[4];
+    int irow[4], rbase[4];
     int2 icol[4];
 #pragma unroll
     for (int I = 0; I < 4; ++I) {
       irow[I] = S.ids[buf][warp][8 * I + g];
+      rbase[I] = irow[I] * PLD;
       icol[I] = *reinterpret_cast<const int2*>(&S.ids[buf][warp][8 * I + 2 * t]);
     }
+    const bool fastg = pooled && n == 32;
     // gather block (I,J): I < 4 covariance block, I == 4 right-hand-side rows
     auto gath = [&](int I, int J) -> double2 {
       if (I == 4) {
@@ -330,18 +456,15 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
         if (g < NR) val = *reinterpret_cast<const double2*>(&S.rhs[buf][warp][g][8 * J + 2 * t]);
         return val;
       }
+      if (fastg) {   // every neighbour slot is live and pooled: plain indexed loads
+        return make_double2(S.PC[rbase[I] + icol[J].x], S.PC[rbase[I] + icol[J].y]);
+      }
       const int row = 8 * I + g, col = 8 * J + 2 * t;
       double c0 = (row == col) ? 1.0 : 0.0, c1 = (row == col + 1) ? 1.0 : 0.0;
       if (pooled) {
         const int ir = irow[I], ix = icol[J].x, iy = icol[J].y;
-        if (ir >= 0 && ix >= 0) {
-          const int hi = max(ir, ix), lo = min(ir, ix);
-          c0 = S.PC[hi * (hi + 1) / 2 + lo];
-        }
-        if (ir >= 0 && iy >= 0) {
-          const int hi = max(ir, iy), lo = min(ir, iy);
-          c1 = S.PC[hi * (hi + 1) / 2 + lo];
-        }
+        if (ir >= 0 && ix >= 0) c0 = S.PC[ir * PLD + ix];
+        if (ir >= 0 && iy >= 0) c1 = S.PC[ir * PLD + iy];
       } else {
         const double xr = S.px[buf][warp][row], yr = S.py[buf][warp][row], zr = DIM3 ? S.pz[buf][warp][row] : 0.0;
         const double2 xc = *reinterpret_cast<const double2*>(&S.px[buf][warp][col]);
@@ -380,15 +503,20 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     };
 
     // ================= column 0 =================
+    TR(0);
     double2 A00 = gath(0, 0);
     post(A00);
+    TR(1);
     P0(grp + gridDim.x);   // next group: index loads in flight during the whole column
     double2 C1 = gath(1, 0), C2 = gath(2, 0), C3 = gath(3, 0), C4 = gath(4, 0);
     double2 D1 = gath(1, 1);
+    TR(2);
     double2 W = waitW();
+    TR(3);
     panel(C1, W);          // L10
     upd(D1, C1, C1);
     post(D1);
+    TR(4);
     P1();                  // next group: record loads
     panel(C2, W);          // L20
     panel(C3, W);          // L30
@@ -405,11 +533,15 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     upd(C3, L30, L10);
     upd(C4, L40, L10);
     upd(D2, L20, L20);
+    TR(5);
     W = waitW();
+    TR(6);
     panel(C2, W);          // L21
     upd(D2, C2, C2);
     post(D2);
-    P23(buf ^ 1);          // next group: RHS rows, hash insert
+    TR(7);
+    P23(buf ^ 1);
+    TR(8);          // next group: RHS rows, hash insert
     panel(C3, W);          // L31
     panel(C4, W);          // L41
     upd(G, C4, C4);
@@ -425,103 +557,41 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     upd(C3, L31, L21);
     upd(C4, L41, L21);
     upd(D3, L31, L31);
+    TR(9);
     bar_sync_sys();        // next group's hash inserts are complete; every PC gather of this group is done
+    TR(10);
     W = waitW();
+    TR(11);
     panel(C3, W);          // L32
     upd(D3, C3, C3);
     post(D3);
-    P4(buf ^ 1);           // next group: pool ids + pooled covariances (overwrites PC)
+    TR(12);
+    P4(buf ^ 1);
+    TR(13);           // next group: pool ids + pooled covariances (overwrites PC)
     panel(C4, W);          // L42
     upd(G, C4, C4);
     // ================= column 3 =================
     upd(Cx, L40, L30);
     upd(Cx, L41, L31);
     upd(Cx, C4, C3);
+    TR(14);
     W = waitW();
+    TR(15);
     panel(Cx, W);          // L43
     upd(G, Cx, Cx);
 
-    // ---- epilogue: G = -B'C^-1B -----------------------------------------------------------
-    *reinterpret_cast<double2*>(&S.exin[warp * EXS + g * 8 + 2 * t]) = G;
-    __syncwarp();
-    if (lane == 0 && c_valid) {
-      const double* Gm = &S.exin[warp * EXS];
-      bool singular = S.flag[warp] != 0;
-      const double uu = -Gm[0], wu = -Gm[8];
-      const double c0 = v.sill;
-      double mean, var;
-      if (NCON == 0) {
-        mean = m.mean + wu;
-        var = c0 - uu;
-      } else {
-        double Gs[NCON > 0 ? NCON * NCON : 1], gq[NCON > 0 ? NCON : 1], hw[NCON > 0 ? NCON : 1];
-#pragma unroll
-        for (int p = 0; p < NCON; ++p) {
-          gq[p] = -Gm[(2 + p) * 8 + 0];
-          hw[p] = -Gm[(2 + p) * 8 + 1];
-#pragma unroll
-          for (int q = 0; q <= p; ++q) Gs[p * NCON + q] = -Gm[(2 + p) * 8 + 2 + q];
-        }
-        if (centered) {
-#pragma unroll
-          for (int p = 0; p < NCON; ++p)
-            gq[p] -= (m.exps[p][0] == 0 && m.exps[p][1] == 0 && m.exps[p][2] == 0) ? 1.0 : 0.0;
-        } else {
-#pragma unroll
-          for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, c_tx, c_ty, c_tz);
-        }
-#pragma unroll
-        for (int j = 0; j < NCON; ++j) {
-          double d = Gs[j * NCON + j];
-          if (!(d > 0.0)) {
-            singular = true;
-            d = 1.0;
-          }
-          const double rs = rsqrt(d);
-          Gs[j * NCON + j] = rs;
-#pragma unroll
-          for (int i = j + 1; i < NCON; ++i) Gs[i * NCON + j] *= rs;
-#pragma unroll
-          for (int i = j + 1; i < NCON; ++i)
-#pragma unroll
-            for (int q = j + 1; q <= i; ++q)
-              Gs[i * NCON + q] = fma(-Gs[i * NCON + j], Gs[q * NCON + j], Gs[i * NCON + q]);
-        }
-        double y[NCON > 0 ? NCON : 1], hy[NCON > 0 ? NCON : 1];
-#pragma unroll
-        for (int i = 0; i < NCON; ++i) {
-          double s1 = gq[i], s2 = hw[i];
-#pragma unroll
-          for (int q = 0; q < i; ++q) {
-            s1 = fma(-Gs[i * NCON + q], y[q], s1);
-            s2 = fma(-Gs[i * NCON + q], hy[q], s2);
-          }
-          y[i] = s1 * Gs[i * NCON + i];
-          hy[i] = s2 * Gs[i * NCON + i];
-        }
-        double gnu = 0.0, hnu = 0.0;
-#pragma unroll
-        for (int i = 0; i < NCON; ++i) {
-          gnu = fma(y[i], y[i], gnu);
-          hnu = fma(hy[i], y[i], hnu);
-        }
-        mean = wu - hnu;
-        var = c0 - uu + gnu;
-      }
-      var += 1e-10;  // krig.jl:278-279
-      if (c_missing) {
-        out_mean[c_tt] = qnan;
-        if (out_var) out_var[c_tt] = qnan;
-        if (out_status) out_status[c_tt] = GSM_ST_MISSING;
-      } else {
-        out_mean[c_tt] = singular ? qnan : mean;
-        if (out_var) out_var[c_tt] = singular ? qnan : var;
-        if (out_status) out_status[c_tt] = singular ? GSM_ST_SINGULAR : GSM_ST_OK;
-      }
+    // ---- hand the trailing Schur block (-B'C^-1B) to the diagonal warp for the epilogue --------
+    *reinterpret_cast<double2*>(&S.Gx[warp * EXS + g * 8 + 2 * t]) = G;
+    if (lane == 0) {
+      S.e_tt[warp] = c_tt;
+      S.e_flags[warp] = (c_valid ? 1 : 0) | (c_missing ? 2 : 0);
     }
+    bar_arrive(BAR_EPI);
     __syncwarp();
+    TR(16);
     bar_sync_sys();        // next group's pooled covariances are complete
     P5();
+    TR(17);
   }
 }
 

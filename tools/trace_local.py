@@ -11,8 +11,8 @@ L.lib_path = lambda: os.path.join(ROOT, "geostatsmodels.jl_b200", "lib", "libgsm
 lib = L.load()
 import torch
 tr = torch.zeros(4 * 9 * 40, dtype=torch.int64, device="cuda")
-lib.gsm_debug_set_trace.argtypes = [C.c_void_p]
-assert lib.gsm_debug_set_trace(tr.data_ptr()) == 0
+lib.gsm_debug_set_trace2.argtypes = [C.c_void_p]
+assert lib.gsm_debug_set_trace2(tr.data_ptr()) == 0
 rng = np.random.default_rng(3)
 n = 200000
 X = rng.uniform(0, 2048, size=(n, 2)); z = rng.standard_normal(n)
@@ -28,11 +28,9 @@ for _ in range(2):
     ctx.local_krige(v, m, t, 32, out_mean=om, out_var=ov, out_status=ost)
 print(ctx.timings())
 T = tr.cpu().numpy().reshape(4, 9, 40)
-names_sys = {0: "start", 1: "gather+rhs", 2: "hash-insert bar", 3: "owner-id bar", 4: "pool eval", 5: "pool bar", 6: "A00 posted",
-             7: "assembled", 24: "epilogue end"}
-for kb in range(4):
-    names_sys.update({8 + kb * 4: f"kb{kb} wait begin", 9 + kb * 4: f"kb{kb} wait end", 10 + kb * 4: f"kb{kb} next posted",
-                      11 + kb * 4: f"kb{kb} updates done"})
+names_sys = {0: "start", 1: "A00 posted", 2: "col0 gathered", 3: "W0", 4: "D1 posted", 5: "col1 prepped", 6: "W1",
+             7: "D2 posted", 8: "P23 done", 9: "col2 prepped", 10: "pool bar1", 11: "W2", 12: "D3 posted", 13: "P4 done",
+             14: "col3 prepped", 15: "W3", 16: "epilogue done", 17: "pool bar2+P5"}
 for it in range(1, 3):
     base = T[it, :8, 0].min()
     print(f"--- iteration {it} (cycles relative to first warp start)")
