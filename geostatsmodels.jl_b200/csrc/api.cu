@@ -412,7 +412,10 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
     cudaEvent_t a = et.mark(st);
     GSM_CHECK(gsm_launch_knn(ctx, tc, maxn, opts->radius, d_pos, d_cnt));
     cudaEvent_t bq = et.mark(st);
-    if (onbr.dev) GSM_CHECK(gsm_launch_nbr_to_rows(ctx, d_pos, tc.count * maxn, onbr.dev + off * maxn));
+    if (onbr.dev) {
+      GSM_CHECK(gsm_launch_sort_lists(ctx, tc, maxn, d_pos, d_cnt));   // lists are promised ascending by (d2, row)
+      GSM_CHECK(gsm_launch_nbr_to_rows(ctx, d_pos, tc.count * maxn, onbr.dev + off * maxn));
+    }
     if (mode == 1) {
       GSM_CHECK(gsm_launch_local_krige(ctx, vd, md, tc, maxn, minn, d_pos, d_cnt, omean.dev + off,
                                        ovar.dev ? ovar.dev + off : nullptr, ostat.dev ? ostat.dev + off : nullptr));

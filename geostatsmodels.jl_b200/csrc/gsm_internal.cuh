@@ -130,6 +130,7 @@ bool gsm_is_device_ptr(const void* p);
 // ---------------------------------------------------------------------------------------------
 int gsm_build_bins(gsm_ctx* ctx);
 int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt);
+int gsm_launch_sort_lists(gsm_ctx* ctx, const TargetsDev& tg, int k, int* d_pos, const int* d_cnt);
 int gsm_launch_nbr_to_rows(gsm_ctx* ctx, const int* d_pos, long long total, int* d_rows);
 int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k,
                            int minneighbors, const int* d_pos, const int* d_cnt, double* d_mean,
@@ -222,6 +223,22 @@ __device__ __forceinline__ double gsm_drift(const ModelDev& m, int n, double x, 
 
 __device__ __forceinline__ double gsm_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double gsm_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+// Ascending sort of one int per lane (bitonic network, 15 compare-exchange steps).  The solve kernels
+// use it to put every neighbour list into a canonical order (ascending record position, unused slots
+// last), so results do not depend on the order in which the search kernel emitted the neighbours.
+__device__ __forceinline__ int gsm_warp_sort_int(int v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = ((lane & k) == 0);          // ascending block?
+      const bool lower = ((lane & j) == 0);        // this lane keeps the smaller element of the pair
+      v = (lower == up) ? min(v, o) : max(v, o);
+    }
+  }
+  return v;
+}
 __device__ __forceinline__ double gsm_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += gsm_shfl_xor(v, o);

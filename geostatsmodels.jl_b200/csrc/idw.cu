@@ -84,6 +84,7 @@ idw_local_kernel(BinsDev b, TargetsDev tg, int k, int minn, double e, int ei, co
   gsm_target_coords(tg, tg.first + t, tx, ty, tz);
   double sw = 0.0, swz = 0.0, hitv = 0.0;
   bool hit = false;
+  int hitrow = 0x7fffffff;
   const int* p = pos + t * (long long)k;
   for (int i = 0; i < n; ++i) {
     const double4 r = b.rec[p[i]];
@@ -93,9 +94,13 @@ idw_local_kernel(BinsDev b, TargetsDev tg, int k, int minn, double e, int ei, co
       const double w = idw_weight<EXPMODE>(d2, e, ei);
       sw += w;
       swz = fma(w, r.w, swz);
-    } else if (!hit) {  // neighbours arrive ascending by (d2,row): the first exact hit is the lowest row
-      hit = true;
-      hitv = r.w;
+    } else {  // exact hit: the FIRST such sample of the reference's ascending (d2,row) list = lowest row
+      const int rw = b.sidx[p[i]];
+      if (rw < hitrow) {
+        hitrow = rw;
+        hit = true;
+        hitv = r.w;
+      }
     }
   }
   out[t] = hit ? hitv : swz / sw;

@@ -1,18 +1,25 @@
 // Exact k-nearest-neighbour search over the grid bins: the B200 replacement for Meshes `search!`
 // on a KNearestSearch / KBallSearch (reference src/models.jl:153-164).
 //
-// One thread per target.  Cells are visited in Chebyshev rings around the target's cell; a max-heap of
-// the best k candidates lives in shared memory with layout [slot][thread] so every lane owns one bank
-// pair and heap traffic is conflict-free whatever slot a lane touches.  The search stops when the
-// current k-th distance is strictly below the distance to the nearest unvisited cell face.
+// One thread walks KNN_RUN consecutive targets.  A max-heap of the best k candidates lives in shared
+// memory with layout [slot][thread] so every lane owns one bank pair and heap traffic is conflict-free
+// whatever slot a lane touches.
+//   cold start : cells are visited in Chebyshev rings around the target's cell until the current k-th
+//                distance is strictly below the distance to the nearest unvisited cell face;
+//   warm start : the previous target's k neighbours are k valid candidates for the next target, so the
+//                largest of their recomputed distances bounds the new k-th distance; only the cells
+//                overlapping that ball are scanned (cell binning is monotone in each coordinate, so the
+//                cell range of [t-R, t+R] contains every sample within R).
 // Total order: ascending (d2, original row); d2 = ((dx*dx+dy*dy)+dz*dz) with every op rounded once
 // (gsm_d2_key) so the selected SET is bit-identical to the oracle's brute-force lexsort.
-// Output per target: positions into the cell-sorted record array, ascending by that order.
+// Output per target: positions into the cell-sorted record array in heap order (a deterministic
+// function of the inputs); sort_lists_kernel orders them ascending when the caller asks for lists.
 #include "gsm_internal.cuh"
 
 namespace {
 
 constexpr int KNN_THREADS = 128;
+constexpr int KNN_RUN = 1;   // consecutive targets per thread (warm start only pays when lanes stay spatially coherent)
 
 struct Heap {
   double* d;  // [k][KNN_THREADS]
@@ -76,111 +83,177 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int* __restrict__ out
   hp.p = reinterpret_cast<int*>(smem_raw + (size_t)k * KNN_THREADS * sizeof(double)) + threadIdx.x;
   hp.k = k;
 
-  long long t = blockIdx.x * (long long)KNN_THREADS + threadIdx.x;
-  if (t >= tg.count) return;
-  double tx, ty, tz;
-  gsm_target_coords(tg, tg.first + t, tx, ty, tz);
-
   const int* __restrict__ cs = b.cell_start;
   const double4* __restrict__ rec = b.rec;
   const int* __restrict__ sidx = b.sidx;
-  const double tc[3] = {tx, ty, tz};
-  int c0[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    int c = (int)floor((tc[d] - b.bbmin[d]) * b.inv_h);
-    c0[d] = min(max(c, 0), b.nc[d] - 1);
-  }
-
-  int cnt = 0;
-  double worst = 1e308 * 10.0;  // +inf
+  const double inf = 1e308 * 10.0;
   const int maxring = max(max(b.nc[0], b.nc[1]), b.nc[2]);
 
-  for (int ring = 0; ring <= maxring; ++ring) {
-    const int zlo = max(c0[2] - ring, 0), zhi = min(c0[2] + ring, b.nc[2] - 1);
-    const int ylo = max(c0[1] - ring, 0), yhi = min(c0[1] + ring, b.nc[1] - 1);
-    const int xlo = max(c0[0] - ring, 0), xhi = min(c0[0] + ring, b.nc[0] - 1);
-    for (int cz = zlo; cz <= zhi; ++cz) {
-      const bool zface = (cz == c0[2] - ring) || (cz == c0[2] + ring);
-      for (int cy = ylo; cy <= yhi; ++cy) {
-        const bool yface = (cy == c0[1] - ring) || (cy == c0[1] + ring);
-        const int rowbase = b.nc[0] * (cy + b.nc[1] * cz);
-        // on a z- or y-face of the shell the whole x-run belongs to the ring; otherwise only its two ends
-        int nseg, segx[2][2];
-        if (zface || yface || ring == 0) {
-          nseg = 1;
-          segx[0][0] = xlo;
-          segx[0][1] = xhi;
-        } else {
-          nseg = 0;
-          if (c0[0] - ring >= 0) {
-            segx[nseg][0] = segx[nseg][1] = c0[0] - ring;
-            nseg++;
-          }
-          if (c0[0] + ring <= b.nc[0] - 1) {
-            segx[nseg][0] = segx[nseg][1] = c0[0] + ring;
-            nseg++;
-          }
+  const long long t0 = (blockIdx.x * (long long)KNN_THREADS + threadIdx.x) * KNN_RUN;
+  int cnt = 0;              // heap fill of the previous target (k when complete)
+  double prev_worst = inf;  // its k-th squared distance
+
+  for (int run = 0; run < KNN_RUN; ++run) {
+    const long long t = t0 + run;
+    if (t >= tg.count) break;
+    double tx, ty, tz;
+    gsm_target_coords(tg, tg.first + t, tx, ty, tz);
+    const double tc[3] = {tx, ty, tz};
+
+    // ---- warm-start bound from the previous target's neighbours ---------------------------------
+    double bound2 = inf;
+    if (cnt == k && run > 0) {
+      double mx = 0.0;
+      for (int i = 0; i < k; ++i) {
+        const double4 r = rec[hp.P(i)];
+        mx = fmax(mx, gsm_d2_key(r.x, r.y, r.z, tx, ty, tz));
+      }
+      if (mx <= 4.0 * prev_worst) bound2 = mx;   // far jump (row wrap, scattered points): search cold
+    }
+    cnt = 0;
+    double worst = inf;
+
+    auto consider = [&](int q) {
+      const double4 r = rec[q];
+      const double d2 = gsm_d2_key(r.x, r.y, r.z, tx, ty, tz);
+      if (d2 > bound2) return;
+      if (cnt < k) {
+        sift_up(hp, cnt, d2, q, sidx);
+        cnt++;
+        if (cnt == k) worst = hp.D(0);
+      } else if (d2 <= worst) {
+        if (key_less(d2, q, hp.D(0), hp.P(0), sidx)) {
+          sift_down(hp, 0, k, d2, q, sidx);
+          worst = hp.D(0);
         }
-        for (int s = 0; s < nseg; ++s) {
-          const int beg = cs[rowbase + segx[s][0]];
-          const int end = cs[rowbase + segx[s][1] + 1];
-          for (int q = beg; q < end; ++q) {
-            const double4 r = rec[q];
-            const double d2 = gsm_d2_key(r.x, r.y, r.z, tx, ty, tz);
-            if (cnt < k) {
-              sift_up(hp, cnt, d2, q, sidx);
-              cnt++;
-              if (cnt == k) worst = hp.D(0);
-            } else if (d2 <= worst) {
-              if (key_less(d2, q, hp.D(0), hp.P(0), sidx)) {
-                sift_down(hp, 0, k, d2, q, sidx);
-                worst = hp.D(0);
+      }
+    };
+
+    if (bound2 < inf) {
+      // ---- warm: scan the cells overlapping the ball of radius R around the target ----------------
+      const double R = __dsqrt_ru(bound2) * (1.0 + 1e-15);
+      int lo[3], hi[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const int a = (int)floor((tc[d] - R - b.bbmin[d]) * b.inv_h);
+        const int e = (int)floor((tc[d] + R - b.bbmin[d]) * b.inv_h);
+        lo[d] = min(max(a, 0), b.nc[d] - 1);
+        hi[d] = min(max(e, 0), b.nc[d] - 1);
+      }
+      for (int cz = lo[2]; cz <= hi[2]; ++cz)
+        for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+          const int rowbase = b.nc[0] * (cy + b.nc[1] * cz);
+          const int beg = cs[rowbase + lo[0]];
+          const int end = cs[rowbase + hi[0] + 1];
+          for (int q = beg; q < end; ++q) consider(q);
+        }
+    } else {
+      // ---- cold: Chebyshev rings around the target's cell ----------------------------------------
+      int c0[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        int c = (int)floor((tc[d] - b.bbmin[d]) * b.inv_h);
+        c0[d] = min(max(c, 0), b.nc[d] - 1);
+      }
+      for (int ring = 0; ring <= maxring; ++ring) {
+        const int zlo = max(c0[2] - ring, 0), zhi = min(c0[2] + ring, b.nc[2] - 1);
+        const int ylo = max(c0[1] - ring, 0), yhi = min(c0[1] + ring, b.nc[1] - 1);
+        const int xlo = max(c0[0] - ring, 0), xhi = min(c0[0] + ring, b.nc[0] - 1);
+        for (int cz = zlo; cz <= zhi; ++cz) {
+          const bool zface = (cz == c0[2] - ring) || (cz == c0[2] + ring);
+          for (int cy = ylo; cy <= yhi; ++cy) {
+            const bool yface = (cy == c0[1] - ring) || (cy == c0[1] + ring);
+            const int rowbase = b.nc[0] * (cy + b.nc[1] * cz);
+            // on a z- or y-face of the shell the whole x-run belongs to the ring; otherwise only its two ends
+            int nseg, segx[2][2];
+            if (zface || yface || ring == 0) {
+              nseg = 1;
+              segx[0][0] = xlo;
+              segx[0][1] = xhi;
+            } else {
+              nseg = 0;
+              if (c0[0] - ring >= 0) {
+                segx[nseg][0] = segx[nseg][1] = c0[0] - ring;
+                nseg++;
               }
+              if (c0[0] + ring <= b.nc[0] - 1) {
+                segx[nseg][0] = segx[nseg][1] = c0[0] + ring;
+                nseg++;
+              }
+            }
+            for (int s = 0; s < nseg; ++s) {
+              const int beg = cs[rowbase + segx[s][0]];
+              const int end = cs[rowbase + segx[s][1] + 1];
+              for (int q = beg; q < end; ++q) consider(q);
             }
           }
         }
-      }
-    }
-    // distance from the target to the nearest face that still has unvisited cells behind it
-    double reach = 1e308 * 10.0;
-    bool any = false;
+        // distance from the target to the nearest face that still has unvisited cells behind it
+        double reach = inf;
+        bool any = false;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      if (c0[d] - ring > 0) {
-        reach = fmin(reach, tc[d] - (b.bbmin[d] + (double)(c0[d] - ring) * b.h));
-        any = true;
-      }
-      if (c0[d] + ring < b.nc[d] - 1) {
-        reach = fmin(reach, (b.bbmin[d] + (double)(c0[d] + ring + 1) * b.h) - tc[d]);
-        any = true;
+        for (int d = 0; d < 3; ++d) {
+          if (c0[d] - ring > 0) {
+            reach = fmin(reach, tc[d] - (b.bbmin[d] + (double)(c0[d] - ring) * b.h));
+            any = true;
+          }
+          if (c0[d] + ring < b.nc[d] - 1) {
+            reach = fmin(reach, (b.bbmin[d] + (double)(c0[d] + ring + 1) * b.h) - tc[d]);
+            any = true;
+          }
+        }
+        if (!any) break;  // every cell visited
+        if (cnt == k) {
+          // conservative margin: a sample can sit a rounding error outside its nominal cell box
+          double safe = reach - 1e-9 * b.h;
+          if (safe > 0.0 && worst < safe * safe) break;
+        }
       }
     }
-    if (!any) break;  // every cell visited
-    if (cnt == k) {
-      // conservative margin: a sample can sit a rounding error outside its nominal cell box
-      double safe = reach - 1e-9 * b.h;
-      if (safe > 0.0 && worst < safe * safe) break;
-    }
-  }
+    prev_worst = (cnt == k) ? worst : inf;
 
-  // heap-sort in place: ascending (d2,row) ends up in slots 0..cnt-1
-  for (int n = cnt - 1; n > 0; --n) {
-    double dl = hp.D(n);
-    int pl = hp.P(n);
-    hp.D(n) = hp.D(0);
-    hp.P(n) = hp.P(0);
-    sift_down(hp, 0, n, dl, pl, sidx);
+    // ---- emit (heap order); KBallSearch keeps neighbours with distance <= radius (models.jl:158) ----
+    int* o = out_pos + t * (long long)k;
+    int nkeep = 0;
+    if (radius > 0.0) {
+      for (int i = 0; i < cnt; ++i)
+        if (__dsqrt_rn(hp.D(i)) <= radius) o[nkeep++] = hp.P(i);
+    } else {
+      for (int i = 0; i < cnt; ++i) o[i] = hp.P(i);
+      nkeep = cnt;
+    }
+    for (int i = nkeep; i < k; ++i) o[i] = -1;
+    out_cnt[t] = nkeep;
   }
-  int nkeep = cnt;
-  if (radius > 0.0) {
-    // KBallSearch (models.jl:158): keep neighbours with distance <= radius (IEEE sqrt like the oracle)
-    nkeep = 0;
-    while (nkeep < cnt && __dsqrt_rn(hp.D(nkeep)) <= radius) nkeep++;
+}
+
+// Ascending (d2, row) order of every neighbour list, in place (only when the caller asks for lists).
+__global__ void sort_lists_kernel(BinsDev b, TargetsDev tg, int k, int* __restrict__ pos, const int* __restrict__ cnt) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= tg.count) return;
+  double tx, ty, tz;
+  gsm_target_coords(tg, tg.first + t, tx, ty, tz);
+  int* p = pos + t * (long long)k;
+  const int n = cnt[t];
+  double key[GSM_MAX_NEIGHBORS];
+  int row[GSM_MAX_NEIGHBORS], pp[GSM_MAX_NEIGHBORS];
+  for (int i = 0; i < n; ++i) {
+    const int q = p[i];
+    const double4 r = b.rec[q];
+    const double d2 = gsm_d2_key(r.x, r.y, r.z, tx, ty, tz);
+    const int rw = b.sidx[q];
+    int j = i - 1;
+    while (j >= 0 && (key[j] > d2 || (key[j] == d2 && row[j] > rw))) {
+      key[j + 1] = key[j];
+      row[j + 1] = row[j];
+      pp[j + 1] = pp[j];
+      --j;
+    }
+    key[j + 1] = d2;
+    row[j + 1] = rw;
+    pp[j + 1] = q;
   }
-  int* o = out_pos + t * (long long)k;
-  for (int i = 0; i < k; ++i) o[i] = i < nkeep ? hp.P(i) : -1;
-  out_cnt[t] = nkeep;
+  for (int i = 0; i < n; ++i) p[i] = pp[i];
 }
 
 __global__ void pos_to_rows_kernel(const int* __restrict__ pos, long long total, const int* __restrict__ sidx,
@@ -196,13 +269,17 @@ __global__ void pos_to_rows_kernel(const int* __restrict__ pos, long long total,
 int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt) {
   if (tg.count <= 0) return GSM_OK;
   size_t smem = (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int));
-  static size_t configured = 0;
-  if (smem > configured) {
-    GSM_CUDA(ctx, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  long long blocks = (tg.count + KNN_THREADS - 1) / KNN_THREADS;
+  GSM_CUDA(ctx, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (tg.count + (long long)KNN_THREADS * KNN_RUN - 1) / ((long long)KNN_THREADS * KNN_RUN);
   knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, d_pos, d_cnt);
+  ctx->tim.launches++;
+  GSM_CUDA(ctx, cudaGetLastError());
+  return GSM_OK;
+}
+
+int gsm_launch_sort_lists(gsm_ctx* ctx, const TargetsDev& tg, int k, int* d_pos, const int* d_cnt) {
+  if (tg.count <= 0) return GSM_OK;
+  sort_lists_kernel<<<(unsigned)((tg.count + 127) / 128), 128, 0, ctx->stream>>>(ctx->bins, tg, k, d_pos, d_cnt);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
   return GSM_OK;

@@ -58,7 +58,11 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   // ---- gather ------------------------------------------------------------------------------
   const bool live = lane < n;
   double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
-  if (live) r = b.rec[pos[t * (long long)k + lane]];
+  {
+    int mypos = lane < k ? pos[t * (long long)k + lane] : -1;
+    const int key = gsm_warp_sort_int(mypos < 0 ? 0x7fffffff : mypos, lane);   // canonical order
+    if (live) r = b.rec[key];
+  }
   sm.px[lane] = r.x;
   sm.py[lane] = r.y;
   sm.pz[lane] = r.z;

@@ -242,10 +242,12 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     const bool live = lane < n;
     double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
     int mypos = -1;
-    if (live) {
-      mypos = pos[tt * (long long)k + lane];
-      r = b.rec[mypos];
+    if (lane < k && valid) mypos = pos[tt * (long long)k + lane];
+    {
+      const int key = gsm_warp_sort_int(mypos < 0 ? 0x7fffffff : mypos, lane);   // canonical order
+      mypos = key == 0x7fffffff ? -1 : key;
     }
+    if (live) r = b.rec[mypos];
     sm.px[lane] = r.x;
     sm.py[lane] = r.y;
     if (DIM3) sm.pz[lane] = r.z;

@@ -41,7 +41,7 @@ constexpr int HSIZE = 512;                 // open-addressing table for de-dupli
 constexpr int BAR_READY = 1, BAR_DONE = 2, BAR_POOL = 3;
 
 __device__ __forceinline__ void dmma(double2& d, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d.x), "+d"(d.y)
                : "d"(a), "d"(b));
 }
@@ -325,8 +325,14 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       if (lane < k) x_pos = pos[x_tt * (long long)k + lane];
     }
   };
+  // canonical neighbour order: ascending record position, unused slots (-1) last
+  auto Psort = [&]() {
+    const int key = gsm_warp_sort_int(x_pos < 0 ? 0x7fffffff : x_pos, lane);
+    x_pos = key == 0x7fffffff ? -1 : key;
+  };
   // P1: neighbour records
   auto P1 = [&]() {
+    Psort();
     x_missing = (x_n < minn) || (x_n <= 0);
     if (x_missing) x_n = 0;
     x_r = make_double4(0.0, 0.0, 0.0, 0.0);
