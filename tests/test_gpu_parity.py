@@ -344,3 +344,65 @@ def test_global_kriging_singular_status(gsm):
     P = np.array([[0.0, 0.0], [1.0, 1.0], [1.0, 1.0], [2.0, 0.5]])
     fm = gsm.fit(gsm.OrdinaryKriging(gsm.SphericalVariogram(range=5.0)), gsm.georef({"z": np.arange(4.0)}, gsm.PointSet(P)))
     assert not gsm.status(fm)
+
+
+def test_uk_quadratic_3d_against_exact_arithmetic(gsm, oracle):
+    """C4-class systems (3-D, k = 32, quadratic drift, dense samples).  The reference factors the saddle
+    matrix with RAW monomials, whose conditioning costs it several digits; the GPU evaluates the same
+    polynomial space centred at the target.  Against 50-digit arithmetic (mpmath) the GPU must hold
+    1e-10 and be at least as close as the float64 oracle."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    o = oracle
+    rng = np.random.default_rng(4)
+    n = 30000
+    X = rng.uniform(0, 64, size=(n, 3))
+    z = np.sin(X[:, 0] / 20) + np.cos(X[:, 2] / 30) + 0.1 * rng.standard_normal(n)
+    P = rng.uniform(8, 56, size=(5, 3))
+    vario = o.Variogram(o.SPHERICAL, 1.0, 0.1, 20.0)
+    om = o.universal_kriging(vario, 2, 3)
+    gm = gsm.UniversalKriging(gsm.SphericalVariogram(sill=1.0, range=20.0, nugget=0.1), 2, 3)
+    got = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), gsm.PointSet(P), maxneighbors=32, prob=True).z
+    mu_o, var_o, _ = o.fitpredict(om, X, z, P, maxneighbors=32, prob=True)
+    alpha = o.scale_factor(vario.range, o.points_absmax(X), o.points_absmax(P))
+    sv = vario.scaled(alpha)
+    exps = o.monomial_exponents(2, 3)
+
+    def cov(h):
+        if h == 0:
+            return mp.mpf(sv.sill)
+        t = h / mp.mpf(sv.range)
+        g = (mp.mpf(sv.sill) - mp.mpf(sv.nugget)) * (mp.mpf("1.5") * t - mp.mpf("0.5") * t ** 3) if h < sv.range \
+            else mp.mpf(sv.sill) - mp.mpf(sv.nugget)
+        return mp.mpf(sv.sill) - (g + mp.mpf(sv.nugget))
+
+    for j in range(len(P)):
+        x0 = P[j] * alpha
+        idx = o.knn(X * alpha, x0, 32)
+        Q = [[mp.mpf(float(c)) for c in row] for row in (X * alpha)[idx]]
+        t0 = [mp.mpf(float(c)) for c in x0]
+        k, p = 32, len(exps)
+        A = mp.matrix(k + p, k + p)
+        r = mp.matrix(k + p, 1)
+        for a in range(k):
+            for b in range(k):
+                A[a, b] = cov(mp.sqrt(sum((Q[a][d] - Q[b][d]) ** 2 for d in range(3))))
+            r[a] = cov(mp.sqrt(sum((Q[a][d] - t0[d]) ** 2 for d in range(3))))
+            for q, e in enumerate(exps):
+                f = mp.mpf(1)
+                for d in range(3):
+                    f *= Q[a][d] ** e[d]
+                A[a, k + q] = f
+                A[k + q, a] = f
+        for q, e in enumerate(exps):
+            f = mp.mpf(1)
+            for d in range(3):
+                f *= t0[d] ** e[d]
+            r[k + q] = f
+        w = mp.lu_solve(A, r)
+        mu_e = sum(w[a] * mp.mpf(float(z[idx[a]])) for a in range(k))
+        var_e = cov(0) - sum(r[a] * w[a] for a in range(k + p)) + mp.mpf("1e-10")
+        err_gpu = max(abs((mp.mpf(float(got.mu[j])) - mu_e) / mu_e), abs((mp.mpf(float(got.sigma[j])) - var_e) / var_e))
+        err_ora = max(abs((mp.mpf(float(mu_o[j])) - mu_e) / mu_e), abs((mp.mpf(float(var_o[j])) - var_e) / var_e))
+        assert err_gpu < 1e-10, (j, float(err_gpu))
+        assert err_gpu <= err_ora * 1.0001 + mp.mpf("1e-15"), (j, float(err_gpu), float(err_ora))
