@@ -19,7 +19,7 @@
 
 #include "gsm_internal.cuh"
 
-#ifdef GSM_TRACE
+#if 0   // superseded by the trace in krige_local_pipe.cuh
 // Developer-only phase trace (make trace): clock64 stamps of CTA 0 for a few group iterations.
 __device__ long long* g_trace = nullptr;
 extern "C" __attribute__((visibility("default"))) int gsm_debug_set_trace(long long* p) {

@@ -15,7 +15,7 @@
 
 #include "gsm_internal.cuh"
 
-#ifdef GSM_TRACE
+#if defined(GSM_TRACE) && GSM_PIPE_DIM3 == 0 && GSM_PIPE_NBC == 4   // developer phase trace: 2-D, k <= 32 unit only
 __device__ long long* g_trace2 = nullptr;
 extern "C" __attribute__((visibility("default"))) int gsm_debug_set_trace2(long long* p) {
   return cudaMemcpyToSymbol(g_trace2, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
@@ -559,14 +559,17 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
 #pragma unroll
         for (int j = 0; j < kb; ++j) upd(Dn, Lb[kb + 1][j], Lb[kb + 1][j]);
       }
+      TR(2 + 4 * kb);
       if (kb == KREL) bar_sync_sys();   // next group's hash inserts complete; last PC gather of this group done
       const double2 W = waitW();
+      TR(3 + 4 * kb);
       if (kb + 1 < NBC) {
         panel(C[kb + 1], W);
         Lb[kb + 1][kb] = C[kb + 1];
         upd(Dn, C[kb + 1], C[kb + 1]);
         post(Dn);
       }
+      TR(4 + 4 * kb);
       // wait-slot work for the next group
       if (NBC >= 3 && kb == 0) P1();
       if ((NBC == 4 && kb == 1) || (NBC == 3 && kb == 0)) P23(buf ^ 1);
@@ -580,6 +583,7 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
       for (int r = 0; r < NRB; ++r)
 #pragma unroll
         for (int q = 0; q <= r; ++q) upd(Gb[r][q], Lb[NBC + r][kb], Lb[NBC + q][kb]);
+      TR(5 + 4 * kb);
     }
 
     // ---- hand the trailing Schur blocks (-B'C^-1B) to the diagonal warp for the epilogue --------
@@ -594,10 +598,10 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     }
     bar_arrive(BAR_EPI);
     __syncwarp();
-    TR(16);
+    TR(18);
     bar_sync_sys();        // next group's pooled covariances are complete
     P5();
-    TR(17);
+    TR(19);
   }
 }
 

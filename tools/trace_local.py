@@ -28,9 +28,9 @@ for _ in range(2):
     ctx.local_krige(v, m, t, 32, out_mean=om, out_var=ov, out_status=ost)
 print(ctx.timings())
 T = tr.cpu().numpy().reshape(4, 9, 40)
-names_sys = {0: "start", 1: "A00 posted", 2: "col0 gathered", 3: "W0", 4: "D1 posted", 5: "col1 prepped", 6: "W1",
-             7: "D2 posted", 8: "P23 done", 9: "col2 prepped", 10: "pool bar1", 11: "W2", 12: "D3 posted", 13: "P4 done",
-             14: "col3 prepped", 15: "W3", 16: "epilogue done", 17: "pool bar2+P5"}
+names_sys = {0: "start", 1: "A00 posted", 18: "G handed off", 19: "pool bar2+P5"}
+for kb in range(4):
+    names_sys.update({2 + 4 * kb: f"col{kb} prepped", 3 + 4 * kb: f"W{kb}", 4 + 4 * kb: f"next diag posted", 5 + 4 * kb: f"col{kb} done"})
 for it in range(1, 3):
     base = T[it, :8, 0].min()
     print(f"--- iteration {it} (cycles relative to first warp start)")
