@@ -609,7 +609,7 @@ template <int NCON, bool DIM3, int NBC>
 int launch_pipe(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k, int minn,
                 int centered, const int* pos, const int* cnt, double* mean, double* var, unsigned char* status) {
   const long long ngroups = (tg.count + SW - 1) / SW;
-  const int per_sm = (2 + NCON > 8) ? 1 : 2;
+  const int per_sm = (sizeof(PipeSmem<2 + NCON>) * 2 <= 220 * 1024) ? 2 : 1;
   const int blocks = (int)std::min<long long>(ngroups, 148LL * per_sm);
   const size_t smem = sizeof(PipeSmem<2 + NCON>);
   auto kern = local_krige_pipe_kernel<NCON, DIM3, NBC>;

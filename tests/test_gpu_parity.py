@@ -407,3 +407,66 @@ def test_uk_quadratic_3d_against_exact_arithmetic(gsm, oracle):
         assert err_gpu < 1e-10, (j, float(err_gpu))
         # at rounding level, or else no worse than the float64 oracle
         assert err_gpu <= max(err_ora, mp.mpf("1e-13")), (j, float(err_gpu), float(err_ora))
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_edge_cases_small_and_degenerate_inputs(gsm, oracle):
+    o = oracle
+    ok = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=5.0, nugget=0.01))
+    om = o.ordinary_kriging(o.Variogram(o.SPHERICAL, 1.0, 0.01, 5.0))
+    # a single sample: every prediction is that value (OK weights sum to one)
+    one = gsm.georef({"z": np.array([3.5])}, gsm.PointSet([(1.0, 2.0)]))
+    pred = gsm.fitpredict(ok, one, gsm.CartesianGrid(4, 3), maxneighbors=32, prob=True).z
+    assert np.allclose(pred.mu, 3.5, rtol=1e-14) and (pred.sigma > 0).all()
+    # two samples, maxneighbors=1 (nearest-sample Kriging), 1-D domain
+    X = np.array([[0.0], [10.0]])
+    z = np.array([1.0, 2.0])
+    P = np.array([[1.0], [4.9], [5.1], [9.0]])
+    got = gsm.fitpredict(ok, gsm.georef({"z": z}, gsm.PointSet(X)), gsm.PointSet(P), maxneighbors=1).z
+    assert np.array_equal(got, np.array([1.0, 1.0, 2.0, 2.0]))
+    # empty target shard
+    t = gsm.Context.grid_targets((0.0, 0.0), (1.0, 1.0), (8, 8), first=10, count=0)
+    c = gsm.Context(0)
+    c.set_samples(np.random.default_rng(0).uniform(size=(50, 2)), np.zeros(50))
+    L = gsm._lib
+    mean, var, st, _ = c.local_krige(L.make_variogram(1, 1.0, 0.0, 1.0), L.make_model(L.GSM_KRIG_ORDINARY), t, 8)
+    assert mean.shape == (0,)
+    c.close()
+    # collinear samples in 2-D (degenerate bounding box in y) and targets far outside the box
+    Xl = np.stack([np.linspace(0, 20, 60), np.zeros(60)], 1)
+    zl = np.sin(Xl[:, 0])
+    Pl = np.array([[5.0, 0.0], [5.0, 3.0], [-40.0, 7.0], [100.0, -100.0]])
+    got = gsm.fitpredict(ok, gsm.georef({"z": zl}, gsm.PointSet(Xl)), gsm.PointSet(Pl), maxneighbors=12, prob=True).z
+    mu, var, _ = o.fitpredict(om, Xl, zl, Pl, maxneighbors=12, prob=True)
+    assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL) and np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL)
+    # duplicate samples with zero nugget: singular local systems surface as status, not as an exception
+    Xd = np.array([[0.0, 0.0], [1.0, 1.0], [1.0, 1.0], [2.0, 0.5], [3.0, 3.0]])
+    c = gsm.Context(0)
+    c.set_samples(Xd, np.arange(5.0))
+    mean, var, st, _ = c.local_krige(L.make_variogram(1, 1.0, 0.0, 10.0), L.make_model(L.GSM_KRIG_ORDINARY),
+                                     gsm.Context.point_targets(np.array([[1.5, 1.0]])), 5)
+    assert st[0] == L.GSM_ST_SINGULAR and np.isnan(mean[0])
+    c.close()
+
+
+def test_large_sample_parity_against_c_oracle(gsm, oracle):
+    """200 k samples, 20 000 scattered targets (the size class of BASELINE config C3) against the C twin of
+    the oracle: neighbour lists bit-exact, mean/variance within 1e-10."""
+    import gsm_oracle_c as oc
+    o = oracle
+    rng = np.random.default_rng(3)
+    n = 200_000
+    X = rng.uniform(0, 2048, size=(n, 2))
+    z = np.sin(X[:, 0] / 20) + np.cos(X[:, 1] / 30) + 0.1 * rng.standard_normal(n)
+    P = rng.uniform(-5, 2053, size=(20_000, 2))
+    om = o.ordinary_kriging(o.Variogram(o.SPHERICAL, 1.0, 0.1, 50.0))
+    gm = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=50.0, sill=1.0, nugget=0.1))
+    mu, var, st, nbr, cnt = oc.fitpredict(om, X, z, P, prob=True, maxneighbors=32, nthreads=8, want_nbr=True)
+    got = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), gsm.PointSet(P), maxneighbors=32, prob=True).z
+    assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL) and np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL)
+    alpha = o.scale_factor(50.0, o.points_absmax(X), o.points_absmax(P))
+    c = gsm.Context(0)
+    c.set_samples(X * alpha, z)
+    idx, k = c.knn(gsm.Context.point_targets(P * alpha), 32)
+    assert np.array_equal(idx, nbr)
+    c.close()
