@@ -370,10 +370,6 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
     gsm_set_error(ctx, "maxneighbors (after clamping to the number of samples) exceeds GSM_MAX_NEIGHBORS");
     return GSM_ERR_UNSUPPORTED;
   }
-  if (mode == 1 && maxn > 32) {
-    gsm_set_error(ctx, "local Kriging supports at most 32 neighbours in this build");
-    return GSM_ERR_UNSUPPORTED;
-  }
   EventTimer et;
   cudaStream_t st = ctx->stream;
   cudaEvent_t e_begin = et.mark(st);

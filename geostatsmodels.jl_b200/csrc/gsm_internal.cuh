@@ -141,6 +141,9 @@ int gsm_launch_local_krige_dmma(gsm_ctx* ctx, const VarioDev& v, const ModelDev&
 int gsm_launch_local_krige_pipe(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                 const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                 double* d_mean, double* d_var, unsigned char* d_status);
+int gsm_launch_local_krige_big(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
+                               const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                               double* d_mean, double* d_var, unsigned char* d_status);
 int gsm_launch_idw_global(gsm_ctx* ctx, double exponent, const TargetsDev& tg, double* d_mean);
 int gsm_launch_idw_local(gsm_ctx* ctx, double exponent, const TargetsDev& tg, int k, int minneighbors,
                          const int* d_pos, const int* d_cnt, double* d_mean, unsigned char* d_status);

@@ -246,10 +246,6 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
                            int minneighbors, const int* d_pos, const int* d_cnt, double* d_mean, double* d_var,
                            unsigned char* d_status) {
   if (tg.count <= 0) return GSM_OK;
-  if (k > 32) {
-    gsm_set_error(ctx, "local Kriging kernel supports maxneighbors <= 32 in this build");
-    return GSM_ERR_UNSUPPORTED;
-  }
   ModelDev m = m_in;
   int ncon = 0;
   if (m.kind == GSM_KRIG_ORDINARY) {  // OK == UK with the single constant drift (ordinary.jl:33-77)
@@ -262,6 +258,9 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool nonconst = false;
   for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
   const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
+  if (k > 32)   // capacity path: one CTA per system, matrix in shared memory
+    return gsm_launch_local_krige_big(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
+                                      d_status);
   // implementation switch for A/B profiling: GSM_LOCAL_IMPL = pipe (default) | dmma | v1
   static const char* impl_env = getenv("GSM_LOCAL_IMPL");
   const std::string impl = impl_env ? impl_env : "pipe";

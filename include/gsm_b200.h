@@ -98,7 +98,8 @@ typedef struct gsm_targets {
 
 /* Options of fitpredictneigh (models.jl:131-198). */
 typedef struct gsm_neighbor_opts {
-  int32_t maxneighbors;   /* clamped like models.jl:144-147 (outside [1,N] -> N, capped at GSM_MAX_NEIGHBORS) */
+  int32_t maxneighbors;   /* clamped like models.jl:144-147 (outside [1,N] -> N); more than GSM_MAX_NEIGHBORS
+                             after clamping -> GSM_ERR_UNSUPPORTED */
   int32_t minneighbors;   /* clamped like models.jl:148-150                                        */
   double radius;          /* > 0: KBallSearch with this (scaled) ball radius (models.jl:158); <= 0: KNearestSearch */
 } gsm_neighbor_opts;

@@ -113,6 +113,9 @@ CASES = [
     ("uk", 1, 3, 1, 32),
     ("uk", 1, 3, 2, 32),
     ("sk", 2, 3, None, 8),
+    ("ok", 1, 2, None, 64),     # 32 < k <= 64: CTA-per-system capacity path
+    ("uk", 1, 3, 1, 48),
+    ("sk", 0, 2, None, 40),
 ]
 
 
