@@ -76,7 +76,8 @@ __device__ __forceinline__ void sift_up(Heap& hp, int i, double d, int p, const 
 }
 
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int* __restrict__ out_pos, int* __restrict__ out_cnt) {
+knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long row0, int ntx,
+           int* __restrict__ out_pos, int* __restrict__ out_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Heap hp;
   hp.d = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
@@ -89,7 +90,20 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int* __restrict__ out
   const double inf = 1e308 * 10.0;
   const int maxring = max(max(b.nc[0], b.nc[1]), b.nc[2]);
 
-  const long long t0 = (blockIdx.x * (long long)KNN_THREADS + threadIdx.x) * KNN_RUN;
+  // Thread -> target map.  Grid targets: a warp covers an 8 x 4 patch of the grid (CTA = 16 x 8), so its
+  // lanes sit in the same one or two cells, walk the same rings and turn candidate loads into broadcasts.
+  // Point targets: consecutive indices.
+  long long t0;
+  if (tiled) {
+    const int tid = threadIdx.x, lx = tid & 7, ly = (tid >> 3) & 3, wq = tid >> 5;
+    const long long bx = blockIdx.x % ntx, by = blockIdx.x / ntx;
+    const long long x = bx * 16 + (wq & 1) * 8 + lx;
+    const long long row = row0 + by * 8 + (wq >> 1) * 4 + ly;
+    const long long lin = row * tg.dims[0] + x;
+    t0 = (x < tg.dims[0] && lin >= tg.first) ? lin - tg.first : tg.count;   // out of range -> skipped below
+  } else {
+    t0 = (blockIdx.x * (long long)KNN_THREADS + threadIdx.x) * KNN_RUN;
+  }
   int cnt = 0;              // heap fill of the previous target (k when complete)
   double prev_worst = inf;  // its k-th squared distance
 
@@ -287,7 +301,17 @@ int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int
   size_t smem = (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int));
   GSM_CUDA(ctx, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long blocks = (tg.count + (long long)KNN_THREADS * KNN_RUN - 1) / ((long long)KNN_THREADS * KNN_RUN);
-  knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, d_pos, d_cnt);
+  int tiled = 0, ntx = 1;
+  long long row0 = 0;
+  if (tg.kind == GSM_TARGETS_GRID && KNN_RUN == 1 && tg.dims[0] >= 8) {
+    tiled = 1;
+    row0 = tg.first / tg.dims[0];
+    const long long rlast = (tg.first + tg.count - 1) / tg.dims[0];
+    ntx = (int)((tg.dims[0] + 15) / 16);
+    blocks = (long long)ntx * ((rlast - row0 + 1 + 7) / 8);
+  }
+  knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, tiled, row0, ntx, d_pos,
+                                                                  d_cnt);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
   return GSM_OK;
