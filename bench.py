@@ -332,7 +332,14 @@ def run_ours(args):
                          "achieved": solve_tflops, "peak": peak, "unit": "TFLOP/s", "frac": solve_tflops / peak,
                          "peak_source": "measured in this run (gsm_measure_fp64_peak: DFMA %.1f, DMMA m8n8k4 %.1f TFLOP/s);"
                                         " MEASURED_PEAKS.json has no FP64 entry" % (fp64_dfma, fp64_dmma),
-                         "flops_per_prediction": fpp, "launch_ms": solve_launch_ms, "traffic": None,
+                         "flops_per_prediction": fpp, "launch_ms": solve_launch_ms,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 systems) from the
+                         # `ncu --set full` capture summarised in profiles/r01_knn_and_local_krige_pipe_ncu_summary.txt;
+                         # algorithmic: 2^20 x (128 B neighbour list + 4 B count + 17 B outputs) = 156 MB
+                         "traffic": 153.4e6, "traffic_unit": "bytes per launch (ncu)",
+                         "algorithmic_flops_per_launch": fpp * min(M, 1 << 20),
+                         "bound_note": "FP64 pipe; on B200 the DMMA (tensor) and DFMA paths are one pipe "
+                                       "(tools/pipebench.cu), so the peak is the larger of the two measured rates",
                          "whole_step_frac": fpp * M * world * steps / (dev_ms * 1e-3) / 1e12 / (peak * world),
                          "hbm": {"algorithmic_bytes_per_prediction": alg_bytes,
                                  "achieved_gbs": alg_bytes * M * steps / (dev_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
