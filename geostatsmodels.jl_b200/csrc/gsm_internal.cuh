@@ -102,6 +102,7 @@ struct gsm_ctx {
   // per-call scratch
   DevBuf nbr_pos;     // chunk x k int : positions into rec
   DevBuf nbr_cnt;     // chunk int
+  DevBuf job_idx;     // job descriptors of the shared-factor local-Kriging kernel
   DevBuf out_mean, out_var, out_status, out_nbr, tgt_points;
 
   // events for gsm_timings
@@ -141,6 +142,9 @@ int gsm_launch_local_krige_dmma(gsm_ctx* ctx, const VarioDev& v, const ModelDev&
 int gsm_launch_local_krige_pipe(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                 const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                 double* d_mean, double* d_var, unsigned char* d_status);
+int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
+                               const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                               double* d_mean, double* d_var, unsigned char* d_status);
 int gsm_launch_local_krige_big(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                double* d_mean, double* d_var, unsigned char* d_status);

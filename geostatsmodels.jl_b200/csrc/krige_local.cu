@@ -262,8 +262,13 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
     return gsm_launch_local_krige_big(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                       d_status);
   // implementation switch for A/B profiling: GSM_LOCAL_IMPL = pipe (default) | dmma | v1
-  static const char* impl_env = getenv("GSM_LOCAL_IMPL");
+  const char* impl_env = getenv("GSM_LOCAL_IMPL");   // read per call: lets one process A/B the kernels
   const std::string impl = impl_env ? impl_env : "pipe";
+  if (impl == "shr") {
+    int rc = gsm_launch_local_krige_shr(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
+                                        d_status);
+    if (rc != GSM_ERR_UNSUPPORTED) return rc;
+  }
   if (impl == "pipe") {
     int rc = gsm_launch_local_krige_pipe(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                          d_status);

@@ -1,0 +1,5 @@
+// Instantiations of the shared-factor local-Kriging kernel: 3-D coordinates, 1 block column(s).
+#define GSM_SHR_DIM3 1
+#define GSM_SHR_NBC 1
+#define GSM_SHR_ENTRY gsm_shr_entry_d1_b1
+#include "krige_local_shr.cuh"

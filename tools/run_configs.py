@@ -111,6 +111,19 @@ def c4():
             **check("c4", pred.z.mu, pred.z.sigma, om, X, z, o.Grid((0.0,) * 3, (1.0,) * 3, grid.dims), 1000, k=32)}
 
 
+def ns():
+    """north-star target: local OK k=32 on 1M samples -> 256^3 grid"""
+    rng = np.random.default_rng(6); n = 1_000_000 // (Q ** 3)
+    X = rng.uniform(0, 256 // Q, size=(n, 3)); z = np.sin(X[:, 0] / 20) + np.cos(X[:, 2] / 30) + 0.1 * rng.standard_normal(n)
+    grid = gsm.CartesianGrid(256 // Q, 256 // Q, 256 // Q)
+    model = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=20.0, sill=1.0, nugget=0.1))
+    pred, dt = timed(lambda: gsm.fitpredict(model, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=32, prob=True, ctx=ctx), reps=2)
+    t = ctx.timings()
+    om = o.ordinary_kriging(o.Variogram(o.SPHERICAL, 1.0, 0.1, 20.0))
+    return {"N": n, "M": grid.nelements(), "e2e_ms": dt * 1e3, "knn_ms": t["knn_ms"], "solve_ms": t["solve_ms"],
+            **check("ns", pred.z.mu, pred.z.sigma, om, X, z, o.Grid((0.0,) * 3, (1.0,) * 3, grid.dims), 1000, k=32)}
+
+
 def c5():
     out = {}
     for dim, dims in ((2, (2048 // Q, 2048 // Q)), (3, (256 // Q,) * 3)):
@@ -130,5 +143,5 @@ def c5():
     return {"M2d": (2048 // Q) ** 2, "M3d": (256 // Q) ** 3, "results": out}
 
 
-for name, fn in (("C1 IDW global", c1), ("C2 OK Gaussian global", c2), ("C3 local OK k=32", c3), ("C4 UK quadratic 3D", c4), ("C5 sweep", c5)):
+for name, fn in (("C1 IDW global", c1), ("C2 OK Gaussian global", c2), ("C3 local OK k=32", c3), ("C4 UK quadratic 3D", c4), ("NS OK 3D 1M->256^3", ns), ("C5 sweep", c5)):
     run(name, fn)
