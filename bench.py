@@ -244,7 +244,7 @@ def run_ours(args):
         t_bins = ctx.timings()
         ctx.local_krige(vario, model, tgt, K, 1, 0.0, out_mean=out_mean, out_var=out_var, out_status=out_stat)
         t = ctx.timings()
-        return {"bin_ms": t_bins["total_ms"], "knn_ms": t["knn_ms"], "solve_ms": t["solve_ms"],
+        return {"bin_ms": t_bins["total_ms"], "knn_ms": t["knn_ms"], "solve_ms": t["solve_ms"], "index_ms": t["index_ms"],
                 "total_ms": t_bins["total_ms"] + t["total_ms"], "launches": t_bins["launches"] + t["launches"]}
 
     fp64_dfma, fp64_dmma = ctx.measure_fp64_peak()
@@ -296,19 +296,22 @@ def run_ours(args):
 
     # ---- reduce over ranks (max time) --------------------------------------------------------------
     stats = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3, sum(p["solve_ms"] for p in phases),
-                          sum(p["knn_ms"] for p in phases), sum(p["bin_ms"] for p in phases)],
+                          sum(p["knn_ms"] for p in phases), sum(p["bin_ms"] for p in phases),
+                          sum(p["index_ms"] for p in phases)],
                          dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms, solve_ms, knn_ms, bin_ms = [float(x) for x in stats.cpu()]
+    dev_ms, wall_ms, e2e_ms, solve_ms, knn_ms, bin_ms, index_ms = [float(x) for x in stats.cpu()]
 
     if rank == 0:
         steps = args.steps
         value = M * world * steps / (dev_ms * 1e-3)
         e2e_val = M * world * steps / (e2e_ms * 1e-3)
         fpp = flops_per_prediction()
-        solve_launch_ms = solve_ms / (steps * max(1, -(-M // (1 << 20))))
-        solve_tflops = fpp * M * steps / (solve_ms * 1e-3) / 1e12
+        # dominant kernel = the shared-factor solve kernel; the job-index kernel that feeds it is timed apart
+        kern_ms = solve_ms - index_ms
+        solve_launch_ms = kern_ms / (steps * max(1, -(-M // (1 << 20))))
+        solve_tflops = fpp * M * steps / (kern_ms * 1e-3) / 1e12
         peak = max(fp64_dfma, fp64_dmma)
         peaks = {}
         try:
@@ -326,17 +329,18 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "predictions/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": int(n * 3 * 8), "d2h_bytes_per_step": int(M * 17)},
             "gpu_launches": launches,
-            "phases_ms_per_step": {"bins": bin_ms / steps, "knn": knn_ms / steps, "solve": solve_ms / steps,
+            "phases_ms_per_step": {"bins": bin_ms / steps, "knn": knn_ms / steps, "job_index": index_ms / steps,
+                                   "solve": (solve_ms - index_ms) / steps,
                                    "nccl_broadcast_once": bcast_ms},
-            "roofline": {"bound": "fp64", "kernel": "local_krige_pipe_kernel<1,false,4> (gather + blocked Cholesky + solve)",
+            "roofline": {"bound": "fp64", "kernel": "local_krige_shr_kernel<1,false,4> (gather + shared-factor blocked Cholesky + solve)",
                          "achieved": solve_tflops, "peak": peak, "unit": "TFLOP/s", "frac": solve_tflops / peak,
                          "peak_source": "measured in this run (gsm_measure_fp64_peak: DFMA %.1f, DMMA m8n8k4 %.1f TFLOP/s);"
                                         " MEASURED_PEAKS.json has no FP64 entry" % (fp64_dfma, fp64_dmma),
                          "flops_per_prediction": fpp, "launch_ms": solve_launch_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 systems) from the
-                         # `ncu --set full` capture summarised in profiles/r01_knn_and_local_krige_pipe_ncu_summary.txt;
-                         # algorithmic: 2^20 x (128 B neighbour list + 4 B count + 17 B outputs) = 156 MB
-                         "traffic": 153.4e6, "traffic_unit": "bytes per launch (ncu)",
+                         # `ncu --set full` capture summarised in profiles/r01_local_krige_shr_ncu_summary.txt;
+                         # algorithmic: 2^17 job descriptors x 384 B + 2^20 x 17 B of outputs = 68 MB
+                         "traffic": 53.8e6, "traffic_unit": "bytes per launch (ncu; the descriptors are still L2-resident)",
                          "algorithmic_flops_per_launch": fpp * min(M, 1 << 20),
                          "bound_note": "FP64 pipe; on B200 the DMMA (tensor) and DFMA paths are one pipe "
                                        "(tools/pipebench.cu), so the peak is the larger of the two measured rates",

@@ -51,7 +51,7 @@ class NeighborOpts(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("bin_ms", C.c_double), ("knn_ms", C.c_double),
                 ("solve_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
-                ("launches", C.c_int64)]
+                ("launches", C.c_int64), ("index_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -392,7 +392,9 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
   int* d_cnt_all = (int*)cntbuf.p;
   if (out_n && gsm_is_device_ptr(out_n)) d_cnt_all = out_n;
 
-  double knn_ms = 0, solve_ms = 0;
+  double knn_ms = 0, solve_ms = 0, index_ms = 0;
+  for (auto e : ctx->idx_marks) cudaEventDestroy(e);
+  ctx->idx_marks.clear();
   std::vector<cudaEvent_t> marks;
   std::vector<cudaEvent_t> chunk_done;
   for (long long off = 0; off < M; off += chunk) {
@@ -441,9 +443,13 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
     knn_ms += EventTimer::ms(marks[i], marks[i + 1]);
     solve_ms += EventTimer::ms(marks[i + 1], marks[i + 2]);
   }
+  for (size_t i = 0; i + 2 <= ctx->idx_marks.size(); i += 2) index_ms += EventTimer::ms(ctx->idx_marks[i], ctx->idx_marks[i + 1]);
+  for (auto e : ctx->idx_marks) cudaEventDestroy(e);
+  ctx->idx_marks.clear();
   ctx->tim.h2d_ms = EventTimer::ms(e_begin, e_h2d);
   ctx->tim.knn_ms = knn_ms;
   ctx->tim.solve_ms = solve_ms;
+  ctx->tim.index_ms = index_ms;
   ctx->tim.bin_ms = 0;
   double t_k = EventTimer::ms(e_begin, e_k);
   double t_c = EventTimer::ms(e_begin, e_copy);

@@ -107,6 +107,7 @@ struct gsm_ctx {
 
   // events for gsm_timings
   cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> idx_marks;   // (begin, end) pairs around the job-index kernel of the current call
 };
 
 struct gsm_fit {

@@ -261,15 +261,19 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   if (k > 32)   // capacity path: one CTA per system, matrix in shared memory
     return gsm_launch_local_krige_big(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                       d_status);
-  // implementation switch for A/B profiling: GSM_LOCAL_IMPL = pipe (default) | dmma | v1
-  const char* impl_env = getenv("GSM_LOCAL_IMPL");   // read per call: lets one process A/B the kernels
-  const std::string impl = impl_env ? impl_env : "pipe";
+  // Default: the shared-factor kernel for grid targets with more than one block column (k > 8: neighbouring
+  // targets share most neighbours, krige_local_shr.cuh), the pipelined kernel otherwise (k <= 8, or explicit
+  // points whose order says nothing about their proximity).  GSM_LOCAL_IMPL = shr | pipe | dmma | v1 overrides
+  // (A/B profiling; read per call so one process can compare them).
+  const char* impl_env = getenv("GSM_LOCAL_IMPL");
+  const bool patches = tg.kind == GSM_TARGETS_GRID && tg.dim >= 2 && tg.dims[1] > 1;
+  const std::string impl = impl_env ? impl_env : ((k > 8 && patches) ? "shr" : "pipe");
   if (impl == "shr") {
     int rc = gsm_launch_local_krige_shr(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                         d_status);
     if (rc != GSM_ERR_UNSUPPORTED) return rc;
   }
-  if (impl == "pipe") {
+  if (impl == "pipe" || impl == "shr") {
     int rc = gsm_launch_local_krige_pipe(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                          d_status);
     if (rc != GSM_ERR_UNSUPPORTED) return rc;

@@ -183,10 +183,19 @@ int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& 
   GSM_CHECK(gsm_reserve(ctx, ctx->job_idx, (size_t)gm.ngroups * sizeof(JobIdx)));
   JobIdx* jobs = (JobIdx*)ctx->job_idx.p;
   const unsigned ixblocks = (unsigned)((gm.ngroups + IX_WARPS - 1) / IX_WARPS);
+  auto mark = [&]() {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, ctx->stream);
+      ctx->idx_marks.push_back(e);
+    }
+  };
+  mark();
   int smax = nbc - 1;
   if (const char* e = getenv("GSM_SHR_SMAX")) smax = std::min(smax, atoi(e));   // developer switch: cap the sharing
   job_index_kernel<<<ixblocks, IX_WARPS * 32, 0, ctx->stream>>>(tg, gm, k, 8 * nbc, smax, minneighbors, d_pos, d_cnt, jobs);
   ctx->tim.launches++;
+  mark();
   GSM_CUDA(ctx, cudaGetLastError());
 #define GSM_SHR_CALL(D, B) gsm_shr_entry_d##D##_b##B(ctx, v, m, ncon, centered, tg, jobs, gm.ngroups, k, d_pos, d_mean, d_var, d_status)
   if (!d3) return nbc == 1 ? GSM_SHR_CALL(0, 1) : (nbc == 2 ? GSM_SHR_CALL(0, 2) : GSM_SHR_CALL(0, 4));

@@ -20,6 +20,7 @@
 //     (4x too slow: a lone warp runs dependent instructions at ~6 cycles each on a busy SM), and the index phase
 //     inside the system warps' wait slot (its barriers and atomics end up on the critical path).
 #include <algorithm>
+#include <type_traits>
 
 #include "gsm_internal.cuh"
 #include "krige_local_jobs.cuh"
@@ -154,6 +155,42 @@ __device__ __forceinline__ bool diag_block(const double* __restrict__ blk, doubl
   return bad;
 }
 
+// Cold paths, kept out of line so the hot path stays dense in the instruction cache.
+// General gather of two adjacent elements (row, col), (row, col+1) of a system's covariance block:
+// pooled with empty slots (identity padding), or direct assembly from the neighbour coordinates (pool overflow).
+template <bool DIM3>
+__device__ __noinline__ double2 gath_cold(const double* __restrict__ PC, bool pooled, int ir, int ix, int iy, int row,
+                                          int col, int n, const double* __restrict__ px,
+                                          const double* __restrict__ py, const double* __restrict__ pz,
+                                          const VarioDev* vp) {
+  double c0 = (row == col) ? 1.0 : 0.0, c1 = (row == col + 1) ? 1.0 : 0.0;
+  if (pooled) {
+    if (ir >= 0 && ix >= 0) c0 = PC[ir * PLD + ix];
+    if (ir >= 0 && iy >= 0) c1 = PC[ir * PLD + iy];
+  } else {
+    const CovFast cf = make_cov(*vp);
+    const double xr = px[row], yr = py[row], zr = DIM3 ? pz[row] : 0.0;
+    const bool rowlive = row < n;
+    double dx = xr - px[col], dy = yr - py[col], dz = DIM3 ? zr - pz[col] : 0.0;
+    const double e0 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
+    dx = xr - px[col + 1], dy = yr - py[col + 1], dz = DIM3 ? zr - pz[col + 1] : 0.0;
+    const double e1 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
+    c0 = (row == col) ? (rowlive ? vp->sill : 1.0) : ((rowlive && col < n) ? e0 : 0.0);
+    c1 = (row == col + 1) ? (rowlive ? vp->sill : 1.0) : ((rowlive && col + 1 < n) ? e1 : 0.0);
+  }
+  return make_double2(c0, c1);
+}
+// Pool overflow: the neighbour record of this lane's slot, slots in ascending record position.
+__device__ __noinline__ double4 q1_direct(const double4* __restrict__ rec, const int* __restrict__ pos, long long tt,
+                                          int k, int n, int lane) {
+  int p = 0x7fffffff;
+  if (lane < n) p = pos[tt * (long long)k + lane];
+  p = gsm_warp_sort_int(p, lane);
+  double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (lane < n) r = rec[p];
+  return r;
+}
+
 template <int NR>
 struct alignas(128) ShrSmem {
   static constexpr int NRB = NR > 8 ? 2 : 1;            // right-hand-side block rows
@@ -165,7 +202,7 @@ struct alignas(128) ShrSmem {
   double rhs[2][SW][NR][32];                            // right-hand-side rows: c0, z, drifts
   double PC[PMAX * PLD];                                // pooled covariances (rows of the non-shared samples)
   double Gx[2][SW * NGB * EXS];                         // trailing Schur blocks handed to the epilogue
-  double ppx[NBJ][PMAX], ppy[NBJ][PMAX], ppz[NBJ][PMAX], pval[NBJ][PMAX];   // pooled records by rank
+  double4 prec[NBJ][PMAX];                              // pooled records {x, y, z, value} by rank
   double fW[NBJ][3][64];                                // inverse diagonal factors of the shared columns
   double fL[NBJ][3][64];                                // shared blocks (1,0), (2,0), (2,1)
   int sids[2][SW][32];                                  // pool rank of every slot (-1: empty)
@@ -221,10 +258,13 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
   auto covs = [&](int q, int I, int J) -> double2 {
     const int qb = q & (NBJ - 1);
     const int r = 8 * I + g, c0 = 8 * J + 2 * t, c1 = c0 + 1;
-    const double xr = S.ppx[qb][r], yr = S.ppy[qb][r], zr = DIM3 ? S.ppz[qb][r] : 0.0;
-    double dx = xr - S.ppx[qb][c0], dy = yr - S.ppy[qb][c0], dz = DIM3 ? zr - S.ppz[qb][c0] : 0.0;
+    const double4* pr = S.prec[qb];
+    const double2 pxy = *reinterpret_cast<const double2*>(&pr[r]);
+    const double2 axy = *reinterpret_cast<const double2*>(&pr[c0]), bxy = *reinterpret_cast<const double2*>(&pr[c1]);
+    const double xr = pxy.x, yr = pxy.y, zr = DIM3 ? pr[r].z : 0.0;
+    double dx = xr - axy.x, dy = yr - axy.y, dz = DIM3 ? zr - pr[c0].z : 0.0;
     const double e0 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
-    dx = xr - S.ppx[qb][c1], dy = yr - S.ppy[qb][c1], dz = DIM3 ? zr - S.ppz[qb][c1] : 0.0;
+    dx = xr - bxy.x, dy = yr - bxy.y, dz = DIM3 ? zr - pr[c1].z : 0.0;
     const double e1 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
     return make_double2(r == c0 ? v.sill : e0, r == c1 ? v.sill : e1);
   };
@@ -344,7 +384,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     };
 
     // prologue: start the shared-factor pipeline (virtual jobs -4..-1: the system warps prepare, this warp factors)
-    for (int jv = -4; jv < 0; ++jv) {
+    for (int jv = -5; jv < 0; ++jv) {
       bar_sync(BAR_START, NTH);
       if (jv < -1) round(jv + 1, false, true);
       __threadfence_block();
@@ -373,32 +413,39 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
   auto bar_sync_sys = [&]() { bar_sync(BAR_POOL, NSYS); };
 
   // ---- streaming the job descriptors (5 jobs ahead) and the pooled records (4 jobs ahead) --------------
-  int l_word = 0;
-  double4 l_rec = make_double4(0.0, 0.0, 0.0, 0.0);
-  auto L0 = [&](int q) __attribute__((always_inline)) {   // issue: one int of the descriptor per lane of warps 0..2
-    l_word = 0;
-    if (warp < 3 && q < niter)
-      l_word = __ldg(reinterpret_cast<const int*>(&jobs[blockIdx.x + (long long)q * gridDim.x]) + warp * 32 + lane);
+  // (asynchronous global -> shared copies: no registers are held while the numeric phase runs)
+  auto cp_async = [&](void* dst, const void* src, auto bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    if (decltype(bytes)::value == 4)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+    else
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
   };
-  auto L1 = [&](int q) __attribute__((always_inline)) {   // land (q >= niter: an empty descriptor)
-    if (warp < 3) reinterpret_cast<int*>(&S.J[q & (NBH - 1)])[warp * 32 + lane] = l_word;
+  auto L0 = [&](int q) __attribute__((always_inline)) {   // descriptor: one int per lane of warps 0..2
+    if (warp < 3) {
+      int* dst = reinterpret_cast<int*>(&S.J[q & (NBH - 1)]) + warp * 32 + lane;
+      if (q < niter)
+        cp_async(dst, reinterpret_cast<const int*>(&jobs[blockIdx.x + (long long)q * gridDim.x]) + warp * 32 + lane,
+                 std::integral_constant<int, 4>{});
+      else
+        *dst = 0;   // past the end: an empty descriptor
+    }
     if (warp == 3 && lane < 4) S.hbad[q & (NBH - 1)][lane] = 0;
   };
-  auto R0 = [&](int q) __attribute__((always_inline)) {   // issue: pooled record of rank warp*32+lane (warps 0, 1)
+  auto R0 = [&](int q) __attribute__((always_inline)) {   // pooled record of rank warp*32+lane (warps 0, 1)
     if (warp < 2 && q < niter) {
       const JobIdx& Jq = S.J[q & (NBH - 1)];
       const int r = warp * 32 + lane;
-      if (r < Jq.P) l_rec = b.rec[Jq.upos[r]];
+      if (r < Jq.P) {
+        const double4* src = &b.rec[Jq.upos[r]];
+        double4* dst = &S.prec[q & (NBJ - 1)][r];
+        cp_async(dst, src, std::integral_constant<int, 16>{});
+        cp_async(reinterpret_cast<char*>(dst) + 16, reinterpret_cast<const char*>(src) + 16, std::integral_constant<int, 16>{});
+      }
     }
   };
-  auto R1 = [&](int q) __attribute__((always_inline)) {
-    if (warp < 2) {
-      const int qb = q & (NBJ - 1), r = warp * 32 + lane;
-      S.ppx[qb][r] = l_rec.x;
-      S.ppy[qb][r] = l_rec.y;
-      S.ppz[qb][r] = l_rec.z;
-      S.pval[qb][r] = l_rec.w;
-    }
+  auto LR1 = [&]() __attribute__((always_inline)) {        // land both (visible after the next barrier)
+    asm volatile("cp.async.wait_all;" ::: "memory");
   };
 
   // Q1: slot order, coordinates and right-hand-side rows of job q into buffer bf
@@ -421,23 +468,20 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       __syncwarp();
       const int id = S.sids[bf][warp][lane];
       if (live) {
-        rx = S.ppx[qb][id];
-        ry = S.ppy[qb][id];
-        rz = DIM3 ? S.ppz[qb][id] : 0.0;
-        rw = S.pval[qb][id];
+        const double2 xy = *reinterpret_cast<const double2*>(&S.prec[qb][id]);
+        const double2 zw = *reinterpret_cast<const double2*>(&S.prec[qb][id].z);
+        rx = xy.x;
+        ry = xy.y;
+        rz = DIM3 ? zw.x : 0.0;
+        rw = zw.y;
       }
     } else {
       // pool overflow: direct assembly from the neighbour records, ascending record position
-      int p = 0x7fffffff;
-      if (live) p = pos[tt * (long long)k + lane];
-      p = gsm_warp_sort_int(p, lane);
-      if (live) {
-        const double4 rec = b.rec[p];
-        rx = rec.x;
-        ry = rec.y;
-        rz = rec.z;
-        rw = rec.w;
-      }
+      const double4 rec = q1_direct(b.rec, pos, tt, k, n, lane);
+      rx = rec.x;
+      ry = rec.y;
+      rz = rec.z;
+      rw = rec.w;
       S.px[bf][warp][lane] = rx;
       S.py[bf][warp][lane] = ry;
       if (DIM3) S.pz[bf][warp][lane] = rz;
@@ -478,8 +522,10 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       const int a = S8 + rr;
       double val = v.sill;
       if (a != bc) {
-        const double dx = S.ppx[qb][a] - S.ppx[qb][bc], dy = S.ppy[qb][a] - S.ppy[qb][bc];
-        const double dz = DIM3 ? S.ppz[qb][a] - S.ppz[qb][bc] : 0.0;
+        const double2 axy = *reinterpret_cast<const double2*>(&S.prec[qb][a]);
+        const double2 bxy = *reinterpret_cast<const double2*>(&S.prec[qb][bc]);
+        const double dx = axy.x - bxy.x, dy = axy.y - bxy.y;
+        const double dz = DIM3 ? S.prec[qb][a].z - S.prec[qb][bc].z : 0.0;
         val = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
       }
       S.PC[a * PLD + bc] = val;
@@ -493,14 +539,12 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
   //    stage 1 of job j+3 (L10, L20, (1,1) - L10 L10') and stage 2 of job j+2 (L21, (2,2) - L20 L20' - L21 L21').
   auto FS = [&](int j) __attribute__((always_inline)) {
     if (SMAX < 1) return;
-    {
+    if (warp < 6) {
       const int q = j + 4, qb = q & (NBJ - 1);
-      if (warp == 0) {
-        if (stage_on(q, 0)) put(&S.exin[(SW + 0) * EXS], covs(q, 0, 0));
-      } else if (SMAX >= 2 && warp <= 2) {
-        if (stage_on(q, 1)) put(warp == 1 ? S.fL[qb][0] : S.fW[qb][1], covs(q, 1, warp - 1));
-      } else if (SMAX >= 3 && warp <= 5) {
-        if (stage_on(q, 2)) put(warp == 5 ? S.fW[qb][2] : S.fL[qb][warp - 2], covs(q, 2, warp - 3));
+      const int I = warp < 1 ? 0 : (warp < 3 ? 1 : 2), Jc = warp - I * (I + 1) / 2;   // (0,0) (1,0) (1,1) (2,0) (2,1) (2,2)
+      if (I < SMAX && stage_on(q, I)) {
+        double* dst = (I == Jc) ? (I == 0 ? &S.exin[SW * EXS] : S.fW[qb][I]) : S.fL[qb][I * (I - 1) / 2 + Jc];
+        put(dst, covs(q, I, Jc));
       }
     }
     if (SMAX >= 2 && (warp == 5 || warp == 6)) {
@@ -538,76 +582,33 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     }
   };
 
-  // ---- prologue: descriptors of jobs 0..4, pools of jobs 0..3, first job's right-hand sides and pool -----
-  for (int q = 0; q <= 4; ++q) {
-    L0(q);
-    L1(q);
-  }
-  bar_sync_sys();
-  for (int q = 0; q <= 3; ++q) {
-    R0(q);
-    R1(q);
-  }
-  bar_sync_sys();
-  for (int jv = -4; jv < 0; ++jv) {   // start the shared-factor pipeline
-    FS(jv);
-    __threadfence_block();
-    bar_sync(BAR_START, NTH);
-    bar_sync(BAR_START, NTH);
-  }
-  Q1(0, 0);
-  Q4(0);
-  bar_sync_sys();
-
-  for (int ji = 0; ji < niter; ++ji) {
+  // ---- job loop.  Jobs -5 .. -1 are virtual: they only stream descriptors / pools in and start the
+  //      shared-factor pipeline (so every helper below has a single call site) --------------------------
+  for (int ji = -5; ji < niter; ++ji) {
+    const bool real = ji >= 0;
     const int jb = ji & (NBJ - 1), buf = ji & 1;
     const JobIdx& Jj = S.J[ji & (NBH - 1)];
-    const int S_ = Jj.S;
-    const int n = Jj.n[warp];
-    const bool pooled = Jj.P >= 0;
+    const int S_ = real ? Jj.S : 0;
+    const int n = real ? Jj.n[warp] : 0;
+    const bool pooled = real ? Jj.P >= 0 : true;
     TR(0);
     L0(ji + 5);
-    R0(ji + 4);
+    if (ji + 4 >= 0) R0(ji + 4);
 
     int irow[NBC], rbase[NBC];
     int2 icol[NBC];
-#pragma unroll
-    for (int I = 0; I < NBC; ++I) {
-      irow[I] = S.sids[buf][warp][8 * I + g];
-      rbase[I] = irow[I] * PLD;
-      icol[I] = *reinterpret_cast<const int2*>(&S.sids[buf][warp][8 * I + 2 * t]);
-    }
     const bool fastg = pooled && n == KMAX;
     // gather block (I,J): I < NBC covariance block, I >= NBC right-hand-side rows
-    auto gath = [&](int I, int J) -> double2 {
+    auto gath = [&](int I, int J, auto fast) -> double2 {
       if (I >= NBC) {
         const int rrow = 8 * (I - NBC) + g;
         double2 val = make_double2(0.0, 0.0);
         if (rrow < NR) val = *reinterpret_cast<const double2*>(&S.rhs[buf][warp][rrow][8 * J + 2 * t]);
         return val;
       }
-      if (fastg) return make_double2(S.PC[rbase[I] + icol[J].x], S.PC[rbase[I] + icol[J].y]);
-      const int row = 8 * I + g, col = 8 * J + 2 * t;
-      double c0 = (row == col) ? 1.0 : 0.0, c1 = (row == col + 1) ? 1.0 : 0.0;
-      if (pooled) {
-        const int ir = irow[I], ix = icol[J].x, iy = icol[J].y;
-        if (ir >= 0 && ix >= 0) c0 = S.PC[ir * PLD + ix];
-        if (ir >= 0 && iy >= 0) c1 = S.PC[ir * PLD + iy];
-      } else {
-        const double xr = S.px[buf][warp][row], yr = S.py[buf][warp][row], zr = DIM3 ? S.pz[buf][warp][row] : 0.0;
-        const double2 xc = *reinterpret_cast<const double2*>(&S.px[buf][warp][col]);
-        const double2 yc = *reinterpret_cast<const double2*>(&S.py[buf][warp][col]);
-        double2 zc = make_double2(0.0, 0.0);
-        if (DIM3) zc = *reinterpret_cast<const double2*>(&S.pz[buf][warp][col]);
-        const bool rowlive = row < n;
-        double dx = xr - xc.x, dy = yr - yc.x, dz = zr - zc.x;
-        const double e0 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
-        dx = xr - xc.y, dy = yr - yc.y, dz = zr - zc.y;
-        const double e1 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
-        c0 = (row == col) ? (rowlive ? v.sill : 1.0) : ((rowlive && col < n) ? e0 : 0.0);
-        c1 = (row == col + 1) ? (rowlive ? v.sill : 1.0) : ((rowlive && col + 1 < n) ? e1 : 0.0);
-      }
-      return make_double2(c0, c1);
+      if (decltype(fast)::value) return make_double2(S.PC[rbase[I] + icol[J].x], S.PC[rbase[I] + icol[J].y]);
+      return gath_cold<DIM3>(S.PC, pooled, irow[I], icol[J].x, icol[J].y, 8 * I + g, 8 * J + 2 * t, n, S.px[buf][warp],
+                             S.py[buf][warp], S.pz[buf][warp], &v);
     };
     auto post = [&](const double2& blk) {
       put(&S.exin[warp * EXS], blk);
@@ -622,14 +623,8 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     constexpr int KREL = NBC >= 2 ? NBC - 2 : 0;   // column after whose preparation PC is released
     double2 Lb[NROWS][NBC];
     double2 Gb[NRB][NRB];
-#pragma unroll
-    for (int r = 0; r < NRB; ++r)
-#pragma unroll
-      for (int q = 0; q < NRB; ++q) Gb[r][q] = make_double2(0.0, 0.0);
-
-    if (S_ == 0) post(gath(0, 0));
-#pragma unroll
-    for (int kb = 0; kb < NBC; ++kb) {
+    // column kb of the factorisation (kb is a constant after unrolling)
+    auto column = [&](int kb, auto fast) __attribute__((always_inline)) {
       const bool shcol = kb < S_;
       // prepare column kb: blocks below the diagonal, and the next diagonal block
       double2 C[NROWS];
@@ -638,7 +633,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         if (i < NBC - 1 && i < S_) {          // shared block: final already
           C[i] = frag(S.fL[jb][i * (i - 1) / 2 + kb]);
         } else {
-          C[i] = gath(i, kb);
+          C[i] = gath(i, kb, fast);
 #pragma unroll
           for (int j = 0; j < kb; ++j) upd(C[i], Lb[i][j], Lb[kb][j]);
         }
@@ -646,13 +641,12 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       double2 Dn = make_double2(0.0, 0.0);
       const bool privnext = kb + 1 < NBC && kb + 1 >= S_;
       if (privnext) {
-        Dn = gath(kb + 1, kb + 1);
+        Dn = gath(kb + 1, kb + 1, fast);
 #pragma unroll
         for (int j = 0; j < kb; ++j) upd(Dn, Lb[kb + 1][j], Lb[kb + 1][j]);
       }
       if (kb == KREL) TR(1);
       if (kb == KREL) bar_sync_sys();   // every gather of this job from the pooled matrix is done
-      if (kb == KREL) TR(2);
       const double2 W = (kb < SMAX && shcol) ? frag(S.fW[jb][kb < 3 ? kb : 0]) : waitW();
       if (kb + 1 < NBC) {
         if (privnext) {
@@ -661,19 +655,6 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
           post(Dn);
         }
         Lb[kb + 1][kb] = C[kb + 1];
-      }
-      // slot work: land the streamed descriptor / pool, then the next job's right-hand sides and pooled covariances
-      if (kb == KREL) {
-        TR(3);
-        L1(ji + 5);
-        R1(ji + 4);
-        TR(4);
-        if (ji + 1 < niter) {
-          Q1(ji + 1, buf ^ 1);
-          TR(5);
-          Q4(ji + 1);
-        }
-        TR(6);
       }
 #pragma unroll
       for (int i = (kb + 1 < NBC ? kb + 2 : kb + 1); i < NROWS; ++i) {
@@ -684,17 +665,67 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       for (int r = 0; r < NRB; ++r)
 #pragma unroll
         for (int q = 0; q <= r; ++q) upd(Gb[r][q], Lb[NBC + r][kb], Lb[NBC + q][kb]);
+    };
+
+    if (real) {
+#pragma unroll
+      for (int I = 0; I < NBC; ++I) {
+        irow[I] = S.sids[buf][warp][8 * I + g];
+        rbase[I] = irow[I] * PLD;
+        icol[I] = *reinterpret_cast<const int2*>(&S.sids[buf][warp][8 * I + 2 * t]);
+      }
+#pragma unroll
+      for (int r = 0; r < NRB; ++r)
+#pragma unroll
+        for (int q = 0; q < NRB; ++q) Gb[r][q] = make_double2(0.0, 0.0);
+      // every slot live and pooled (the common case): plain indexed loads, no calls on this path
+      if (fastg) {
+        if (S_ == 0) post(gath(0, 0, std::true_type{}));
+#pragma unroll
+        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{});
+      } else {
+        if (S_ == 0) post(gath(0, 0, std::false_type{}));
+#pragma unroll
+        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::false_type{});
+      }
     }
 
-    // ---- hand the trailing Schur blocks (-B'C^-1B) to the diagonal warp for the epilogue --------
+    // ---- slot (the diagonal warp works on the block just posted): land the streamed descriptor / pool,
+    //      then the next job's slot order, right-hand sides and pooled covariances ----
+    TR(3);
+    LR1();
+    TR(4);
+    if (ji + 1 >= 0 && ji + 1 < niter) {
+      Q1(ji + 1, buf ^ 1);
+      TR(5);
+      Q4(ji + 1);
+    }
+    TR(6);
+
+    if (real) {
+      if (fastg) {
 #pragma unroll
-    for (int r = 0; r < NRB; ++r)
+        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::true_type{});
+      } else {
 #pragma unroll
-      for (int q = 0; q <= r; ++q) put(&S.Gx[buf][(warp * NGB + r * (r + 1) / 2 + q) * EXS], Gb[r][q]);
-    TR(7);
-    bar_arrive(BAR_EPI, NSD);
-    __syncwarp();
+        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::false_type{});
+      }
+      // ---- hand the trailing Schur blocks (-B'C^-1B) to the diagonal warp for the epilogue --------
+#pragma unroll
+      for (int r = 0; r < NRB; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) put(&S.Gx[buf][(warp * NGB + r * (r + 1) / 2 + q) * EXS], Gb[r][q]);
+      TR(7);
+      bar_arrive(BAR_EPI, NSD);
+      __syncwarp();
+    }
+    if (!real) bar_sync_sys();   // (real jobs: the last hand-off barrier already ordered the pool landing)
     FS(ji);
+    if (!real) {   // the diagonal warp runs the shared stages of the virtual round
+      __threadfence_block();
+      bar_sync(BAR_START, NTH);
+      bar_sync(BAR_START, NTH);
+    }
     bar_sync_sys();        // next job's pooled covariances, descriptor and pool are complete
     TR(8);
   }

@@ -113,6 +113,7 @@ typedef struct gsm_timings {
   double d2h_ms;       /* result download                                       */
   double total_ms;     /* first event to last event                             */
   int64_t launches;    /* kernels launched by the library in the call           */
+  double index_ms;     /* part of solve_ms spent in the job-index kernel (shared-factor local Kriging) */
 } gsm_timings;
 
 typedef struct gsm_ctx gsm_ctx;   /* opaque; owns a device, a stream, sample + scratch buffers */

@@ -224,9 +224,11 @@ def test_minneighbors_missing_and_shards(gsm, oracle):
     whole = gsm.fitpredict(ok, tab, grid, maxneighbors=16, prob=True).z
     parts = [gsm.fitpredict(ok, tab, grid, maxneighbors=16, prob=True, first=f, count=c).z
              for f, c in ((0, 100), (100, 77), (177, 123))]
-    # neighbour lists are put in a canonical order before assembly, so sharding does not change a single bit
-    assert np.array_equal(np.concatenate([p.mu for p in parts]), whole.mu)
-    assert np.array_equal(np.concatenate([p.sigma for p in parts]), whole.sigma)
+    # every system is assembled in a canonical order (samples shared by its 4 x 2 patch first, then ascending
+    # record position); a shard boundary that cuts a patch can change which samples count as shared, so the
+    # guarantee is agreement to rounding, not bit-equality
+    assert np.allclose(np.concatenate([p.mu for p in parts]), whole.mu, rtol=1e-12, atol=1e-13)
+    assert np.allclose(np.concatenate([p.sigma for p in parts]), whole.sigma, rtol=1e-12, atol=1e-13)
 
 
 # ------------------------------------------------------------------------------------------- IDW
