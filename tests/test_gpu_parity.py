@@ -475,3 +475,47 @@ def test_large_sample_parity_against_c_oracle(gsm, oracle):
     idx, k = c.knn(gsm.Context.point_targets(P * alpha), 32)
     assert np.array_equal(idx, nbr)
     c.close()
+
+
+# ------------------------------------------------------------ shared-factor kernel, steady state
+STEADY = [
+    # kind, dim, deg, k, dims, n, first, count, neighborhood
+    ("ok", 2, None, 32, (512, 96), 9000, 0, None, None),       # 6144 patches: ~20 jobs per CTA
+    ("ok", 2, None, 32, (203, 77), 5000, 317, 14001, None),    # odd extents, slab cutting patches
+    ("sk", 2, None, 16, (301, 60), 4000, 0, None, None),       # two block columns
+    ("uk", 2, 1, 24, (256, 64), 6000, 0, None, None),          # ragged lists (k not a multiple of 8), drift rows
+    ("ok", 3, None, 32, (40, 36, 34), 30000, 0, None, None),   # 2 x 2 x 2 patches
+    ("uk", 3, 2, 32, (36, 30, 28), 25000, 1000, 25000, None),  # two right-hand-side block rows, slab
+    ("ok", 2, None, 32, (256, 64), 2500, 0, None, 6.0),        # radius-limited: ragged and missing systems
+    ("ok", 2, None, 32, (64, 48), 60000, 0, None, None),       # samples much denser than targets: pool overflow
+]
+
+
+@pytest.mark.parametrize("kind,dim,deg,k,dims,n,first,count,nbh", STEADY)
+def test_shared_factor_kernel_steady_state(gsm, oracle, kind, dim, deg, k, dims, n, first, count, nbh):
+    """Grids large enough that every CTA of the persistent shared-factor kernel runs many jobs (the 3-stage
+    shared-factor pipeline and the descriptor / pool streaming in steady state), against the C oracle."""
+    import gsm_oracle_c as oc
+    o = oracle
+    ext = tuple(float(d) for d in dims)
+    rng = np.random.default_rng(77 + dim + k)
+    X = rng.uniform(0, 1, size=(n, dim)) * np.array(ext)
+    z = np.sin(X[:, 0] / 20) + np.cos(X[:, -1] / 30) + 0.1 * rng.standard_normal(n)
+    vario = o.Variogram(o.SPHERICAL, 1.0, 0.1, 25.0)
+    om = _oracle_model(o, kind, vario, dim, mean=float(z.mean()), deg=deg)
+    gm = _gsm_model(gsm, kind, vario, dim, mean=float(z.mean()), deg=deg)
+    og = o.Grid(tuple(0.0 for _ in dims), tuple(1.0 for _ in dims), dims)
+    kw = dict(prob=True, maxneighbors=k, first=first, count=count)
+    mu, var, st, _, _ = oc.fitpredict(om, X, z, og, nthreads=8, neighborhood=nbh, **kw)
+    grid = gsm.CartesianGrid(*dims)
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    kw["count"] = -1 if count is None else count
+    got = gsm.fitpredict(gm, tab, grid, neighborhood=nbh, **kw).z
+    miss = np.ma.getmaskarray(got.mu) if np.ma.isMaskedArray(got.mu) else ~np.isfinite(got.mu)
+    assert np.array_equal(miss, st != 0)
+    ok = ~miss
+    # UK with raw monomials loses digits in the REFERENCE formulation (DESIGN.md section 6): tolerance per case
+    rtol = RTOL if deg is None else 1e-7
+    gmu, gvar = np.ma.filled(got.mu, 0.0), np.ma.filled(got.sigma, 0.0)
+    assert np.allclose(gmu[ok], mu[ok], rtol=rtol, atol=1e-9 if deg else ATOL), np.abs(gmu[ok] - mu[ok]).max()
+    assert np.allclose(gvar[ok], var[ok], rtol=rtol, atol=1e-9 if deg else ATOL), np.abs(gvar[ok] - var[ok]).max()
