@@ -21,7 +21,7 @@ GSM_KRIG_SIMPLE, GSM_KRIG_ORDINARY, GSM_KRIG_UNIVERSAL = 0, 1, 2
 GSM_TARGETS_GRID, GSM_TARGETS_POINTS = 0, 1
 
 EXPORTED_SYMBOLS = [
-    "gsm_abi_version", "gsm_create", "gsm_destroy", "gsm_last_error", "gsm_get_timings", "gsm_synchronize",
+    "gsm_abi_version", "gsm_create", "gsm_destroy", "gsm_last_error", "gsm_get_timings", "gsm_get_summary", "gsm_synchronize",
     "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_knn", "gsm_local_krige",
     "gsm_global_krige_fit", "gsm_global_krige_status", "gsm_global_krige_predict", "gsm_global_krige_free",
     "gsm_idw", "gsm_measure_fp64_peak",
@@ -46,6 +46,10 @@ class Targets(C.Structure):
 
 class NeighborOpts(C.Structure):
     _fields_ = [("maxneighbors", C.c_int32), ("minneighbors", C.c_int32), ("radius", C.c_double)]
+
+
+class Summary(C.Structure):
+    _fields_ = [("missing", C.c_int64), ("singular", C.c_int64), ("nonpositive_var", C.c_int64), ("total", C.c_int64)]
 
 
 class Timings(C.Structure):
@@ -88,6 +92,7 @@ def load():
     lib.gsm_last_error.argtypes = [vp]
     lib.gsm_last_error.restype = C.c_char_p
     lib.gsm_get_timings.argtypes = [vp, P(Timings)]
+    lib.gsm_get_summary.argtypes = [vp, P(Summary)]
     lib.gsm_synchronize.argtypes = [vp]
     lib.gsm_host_alloc.argtypes = [P(vp), i64]
     lib.gsm_host_free.argtypes = [vp]
@@ -183,6 +188,12 @@ class Context:
         t = Timings()
         self._check(self._lib.gsm_get_timings(self._h, C.byref(t)))
         return t.asdict()
+
+    def summary(self) -> dict:
+        """status counts of the last neighbourhood call, reduced on the device (total = -1: not available)"""
+        sm = Summary()
+        self._check(self._lib.gsm_get_summary(self._h, C.byref(sm)))
+        return {k: getattr(sm, k) for k, _ in sm._fields_}
 
     def synchronize(self):
         self._check(self._lib.gsm_synchronize(self._h))

@@ -444,10 +444,16 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             mean, var = gfit.predict(t, want_var=prob)
             st = np.zeros(M, dtype=np.uint8)
             gfit.close()
-        # one pass over the status bytes decides everything (the columns are tens of MB)
-        clean = not st.any()
+        # the library reduces the status / variance columns on the device (gsm_get_summary): the host only
+        # scans them (tens of MB) when that is not available
+        sm = ctx.summary() if neighbors else {"total": -1}
+        known = sm["total"] == M
+        clean = (sm["missing"] == 0 and sm["singular"] == 0) if known else not st.any()
         if prob:
-            bad = (var.min() <= 0) if clean else bool(np.any((var <= 0) & (st == 0)))
+            if known:
+                bad = sm["nonpositive_var"] > 0
+            else:
+                bad = (var.min() <= 0) if clean else bool(np.any((var <= 0) & (st == 0)))
             if bad:
                 raise ValueError("PosDefException: non-positive Kriging variance")  # MvNormal(mu, Sigma), krig.jl:236
             # Normal.(mean, var), models.jl:298-299

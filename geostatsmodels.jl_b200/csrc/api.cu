@@ -205,6 +205,26 @@ struct OutBuf {
 
 constexpr long long CHUNK = 1LL << 20;  // targets per kernel wave (bounds the neighbour scratch)
 
+// status / variance summary of one chunk (gsm_summary): counts land in c[0..2]
+__global__ void summary_kernel(const unsigned char* __restrict__ st, const double* __restrict__ var, long long n,
+                               unsigned long long* __restrict__ c) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  int miss = 0, sing = 0, nonpos = 0;
+  if (i < n) {
+    const int s = st[i];
+    miss = s == GSM_ST_MISSING;
+    sing = s == GSM_ST_SINGULAR;
+    nonpos = (var != nullptr && s == GSM_ST_OK && !(var[i] > 0.0)) ? 1 : 0;
+  }
+  const unsigned m0 = __ballot_sync(0xffffffffu, miss), m1 = __ballot_sync(0xffffffffu, sing),
+                 m2 = __ballot_sync(0xffffffffu, nonpos);
+  if ((threadIdx.x & 31) == 0) {
+    if (m0) atomicAdd(&c[0], (unsigned long long)__popc(m0));
+    if (m1) atomicAdd(&c[1], (unsigned long long)__popc(m1));
+    if (m2) atomicAdd(&c[2], (unsigned long long)__popc(m2));
+  }
+}
+
 struct EventTimer {
   std::vector<cudaEvent_t> evs;
   cudaEvent_t mark(cudaStream_t st) {
@@ -265,7 +285,7 @@ int gsm_destroy(gsm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->coords, &ctx->values, &ctx->rec, &ctx->sidx, &ctx->cell_of, &ctx->cell_start,
-                    &ctx->cell_fill, &ctx->cub_tmp, &ctx->red, &ctx->nbr_pos, &ctx->nbr_cnt, &ctx->job_idx, &ctx->out_mean,
+                    &ctx->cell_fill, &ctx->cub_tmp, &ctx->red, &ctx->nbr_pos, &ctx->nbr_cnt, &ctx->job_idx, &ctx->summ_dev, &ctx->out_mean,
                     &ctx->out_var, &ctx->out_status, &ctx->out_nbr, &ctx->tgt_points};
   for (DevBuf* b : bufs) free_buf(*b);
   cudaStreamDestroy(ctx->stream);
@@ -275,6 +295,12 @@ int gsm_destroy(gsm_ctx* ctx) {
 }
 
 const char* gsm_last_error(const gsm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gsm_get_summary(const gsm_ctx* ctx, gsm_summary* out) {
+  if (!ctx || !out) return GSM_ERR_INVALID;
+  *out = ctx->summ;
+  return GSM_OK;
+}
 
 int gsm_get_timings(const gsm_ctx* ctx, gsm_timings* out) {
   if (!ctx || !out) return GSM_ERR_INVALID;
@@ -392,6 +418,10 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
   int* d_cnt_all = (int*)cntbuf.p;
   if (out_n && gsm_is_device_ptr(out_n)) d_cnt_all = out_n;
 
+  GSM_CHECK(gsm_reserve(ctx, ctx->summ_dev, 4 * sizeof(unsigned long long)));
+  unsigned long long* d_summ = (unsigned long long*)ctx->summ_dev.p;
+  GSM_CUDA(ctx, cudaMemsetAsync(d_summ, 0, 4 * sizeof(unsigned long long), st));
+  ctx->summ = gsm_summary{0, 0, 0, -1};
   double knn_ms = 0, solve_ms = 0, index_ms = 0;
   for (auto e : ctx->idx_marks) cudaEventDestroy(e);
   ctx->idx_marks.clear();
@@ -422,6 +452,11 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
                                      ostat.dev ? ostat.dev + off : nullptr));
     }
     cudaEvent_t c = et.mark(st);
+    if (mode != 0 && ostat.dev) {   // (after the solve mark: not part of solve_ms)
+      summary_kernel<<<(unsigned)((tc.count + 255) / 256), 256, 0, st>>>(ostat.dev + off, ovar.dev ? ovar.dev + off : nullptr,
+                                                                       tc.count, d_summ);
+      ctx->tim.launches++;
+    }
     marks.push_back(a);
     marks.push_back(bq);
     marks.push_back(c);
@@ -446,6 +481,11 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
   for (size_t i = 0; i + 2 <= ctx->idx_marks.size(); i += 2) index_ms += EventTimer::ms(ctx->idx_marks[i], ctx->idx_marks[i + 1]);
   for (auto e : ctx->idx_marks) cudaEventDestroy(e);
   ctx->idx_marks.clear();
+  if (mode != 0 && ostat.dev) {
+    unsigned long long hs[4] = {0, 0, 0, 0};
+    GSM_CUDA(ctx, cudaMemcpy(hs, d_summ, sizeof(hs), cudaMemcpyDeviceToHost));
+    ctx->summ = gsm_summary{(int64_t)hs[0], (int64_t)hs[1], (int64_t)hs[2], (int64_t)M};
+  }
   ctx->tim.h2d_ms = EventTimer::ms(e_begin, e_h2d);
   ctx->tim.knn_ms = knn_ms;
   ctx->tim.solve_ms = solve_ms;

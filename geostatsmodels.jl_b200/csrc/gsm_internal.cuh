@@ -83,6 +83,7 @@ struct gsm_ctx {
   cudaStream_t copy_stream = nullptr;  // D2H overlap
   std::string err;
   gsm_timings tim{};
+  gsm_summary summ{};
 
   // samples
   int dim = 0;
@@ -103,6 +104,7 @@ struct gsm_ctx {
   DevBuf nbr_pos;     // chunk x k int : positions into rec
   DevBuf nbr_cnt;     // chunk int
   DevBuf job_idx;     // job descriptors of the shared-factor local-Kriging kernel
+  DevBuf summ_dev;    // 4 x u64 status counters of the current call
   DevBuf out_mean, out_var, out_status, out_nbr, tgt_points;
 
   // events for gsm_timings

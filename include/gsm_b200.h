@@ -116,6 +116,17 @@ typedef struct gsm_timings {
   double index_ms;     /* part of solve_ms spent in the job-index kernel (shared-factor local Kriging) */
 } gsm_timings;
 
+/* Per-target status counts of the last neighbourhood call (reduced on the device, so a host that only needs
+ * "did anything go wrong" does not have to scan the status / variance columns).  The reference raises on a
+ * non-positive variance when it builds Normal(mean, var) (models.jl:298-299): nonpositive_var counts the
+ * targets with status OK whose variance is not > 0.  total = targets covered, -1 when no status was produced. */
+typedef struct gsm_summary {
+  int64_t missing;
+  int64_t singular;
+  int64_t nonpositive_var;
+  int64_t total;
+} gsm_summary;
+
 typedef struct gsm_ctx gsm_ctx;   /* opaque; owns a device, a stream, sample + scratch buffers */
 typedef struct gsm_fit gsm_fit;   /* opaque; a fitted global Kriging model (FittedKriging)     */
 
@@ -126,6 +137,7 @@ GSM_API int gsm_destroy(gsm_ctx* ctx);
 /* Message of the last error on this context (or of the last failed gsm_create when ctx == NULL). */
 GSM_API const char* gsm_last_error(const gsm_ctx* ctx);
 GSM_API int gsm_get_timings(const gsm_ctx* ctx, gsm_timings* out);
+GSM_API int gsm_get_summary(const gsm_ctx* ctx, gsm_summary* out);
 GSM_API int gsm_synchronize(gsm_ctx* ctx);
 
 /* Pinned host buffers so outputs DMA straight into caller-owned memory (Julia: unsafe_wrap). */

@@ -219,6 +219,11 @@ def test_minneighbors_missing_and_shards(gsm, oracle):
     assert np.array_equal(miss, st == 1) and miss[-1]
     assert np.allclose(np.ma.filled(got.mu, 0)[~miss], mu[~miss], rtol=RTOL, atol=ATOL)
     assert np.allclose(np.ma.filled(got.sigma, 0)[~miss], var[~miss], rtol=RTOL, atol=ATOL)
+    # the device-side summary (gsm_get_summary) agrees with the status column
+    c = gsm.default_context()
+    sm = c.summary()
+    assert sm["total"] == st.size and sm["missing"] == int((st == 1).sum()) and sm["singular"] == int((st == 2).sum())
+    assert sm["nonpositive_var"] == 0
     # shards of a grid concatenate to the whole domain
     grid = gsm.CartesianGrid((0.0, 0.0), (60.0, 60.0), dims=(20, 15))
     whole = gsm.fitpredict(ok, tab, grid, maxneighbors=16, prob=True).z
