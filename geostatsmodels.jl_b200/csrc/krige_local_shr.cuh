@@ -624,13 +624,15 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     double2 Lb[NROWS][NBC];
     double2 Gb[NRB][NRB];
     // column kb of the factorisation (kb is a constant after unrolling)
-    auto column = [&](int kb, auto fast) __attribute__((always_inline)) {
-      const bool shcol = kb < S_;
+    auto column = [&](int kb, auto fast, auto sfix) __attribute__((always_inline)) {
+      // Sx: the number of shared block columns, a compile-time constant on the specialised path
+      const int Sx = decltype(sfix)::value >= 0 ? decltype(sfix)::value : S_;
+      const bool shcol = kb < Sx;
       // prepare column kb: blocks below the diagonal, and the next diagonal block
       double2 C[NROWS];
 #pragma unroll
       for (int i = kb + 1; i < NROWS; ++i) {
-        if (i < NBC - 1 && i < S_) {          // shared block: final already
+        if (i < NBC - 1 && i < Sx) {          // shared block: final already
           C[i] = frag(S.fL[jb][i * (i - 1) / 2 + kb]);
         } else {
           C[i] = gath(i, kb, fast);
@@ -639,7 +641,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         }
       }
       double2 Dn = make_double2(0.0, 0.0);
-      const bool privnext = kb + 1 < NBC && kb + 1 >= S_;
+      const bool privnext = kb + 1 < NBC && kb + 1 >= Sx;
       if (privnext) {
         Dn = gath(kb + 1, kb + 1, fast);
 #pragma unroll
@@ -658,7 +660,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       }
 #pragma unroll
       for (int i = (kb + 1 < NBC ? kb + 2 : kb + 1); i < NROWS; ++i) {
-        if (!(i < NBC - 1 && i < S_)) panel(C[i], W);
+        if (!(i < NBC - 1 && i < Sx)) panel(C[i], W);
         Lb[i][kb] = C[i];
       }
 #pragma unroll
@@ -679,14 +681,19 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < NRB; ++q) Gb[r][q] = make_double2(0.0, 0.0);
       // every slot live and pooled (the common case): plain indexed loads, no calls on this path
-      if (fastg) {
+      using SFull = std::integral_constant<int, SMAX>;
+      using SAny = std::integral_constant<int, -1>;
+      if (fastg && SMAX > 0 && S_ == SMAX) {   // the common case, fully specialised: straight-line code
+#pragma unroll
+        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{}, SFull{});
+      } else if (fastg) {
         if (S_ == 0) post(gath(0, 0, std::true_type{}));
 #pragma unroll
-        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{});
+        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{}, SAny{});
       } else {
         if (S_ == 0) post(gath(0, 0, std::false_type{}));
 #pragma unroll
-        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::false_type{});
+        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::false_type{}, SAny{});
       }
     }
 
@@ -703,12 +710,17 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     TR(6);
 
     if (real) {
-      if (fastg) {
+      using SFull = std::integral_constant<int, SMAX>;
+      using SAny = std::integral_constant<int, -1>;
+      if (fastg && SMAX > 0 && S_ == SMAX) {
 #pragma unroll
-        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::true_type{});
+        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::true_type{}, SFull{});
+      } else if (fastg) {
+#pragma unroll
+        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::true_type{}, SAny{});
       } else {
 #pragma unroll
-        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::false_type{});
+        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::false_type{}, SAny{});
       }
       // ---- hand the trailing Schur blocks (-B'C^-1B) to the diagonal warp for the epilogue --------
 #pragma unroll
