@@ -3,7 +3,7 @@
 // turns the 8 neighbour lists of a patch (models.jl:162-184: one search per target) into
 //   * the pool of distinct samples of the patch, RANKED: samples common to every active member first, then
 //     ascending record position -- the canonical slot order of every system of the patch,
-//   * one 64-bit membership mask per member (bit r: pooled sample of rank r is a neighbour),
+//   * the slot order of every member (pool ranks ascending) and the integer grid coordinates of its target,
 //   * S, the number of 8-wide block columns all members share.
 #pragma once
 #include "gsm_internal.cuh"
@@ -11,16 +11,18 @@
 constexpr int GSM_JOB_PMAX = 64;   // pool capacity; a larger union is solved by direct assembly (P = -1)
 
 struct alignas(128) JobIdx {
-  unsigned long long mask[8];      // pool ranks of each member's neighbours
+  unsigned char sid[8][32];        // pool rank of every slot of every member, canonical order (255: empty slot)
   int P;                           // distinct samples (0..64); -1: the union does not fit the pool
   int S;                           // shared leading block columns (8 samples each)
   unsigned char n[8];              // neighbours per member (0: missing / none)
   unsigned char fl[8];             // bit 0: write a result, bit 1: missing (fewer than minneighbors)
   int tt[8];                       // relative target index of each member (-1: none)
-  int pad[2];
+  int ci[8][3];                    // grid index of each member's target (grid targets only)
+  int pad[26];
   int upos[GSM_JOB_PMAX];          // record position of every pooled sample, by rank
 };
-static_assert(sizeof(JobIdx) == 384, "JobIdx layout");
+static_assert(sizeof(JobIdx) == 768, "JobIdx layout");
+constexpr int GSM_JOB_WORDS = sizeof(JobIdx) / 4;   // 192 = 6 warps x 32 lanes
 
 // Patch enumeration of one launch (a contiguous slab [first, first + count) of the target domain).
 struct GroupMap {
@@ -34,7 +36,9 @@ struct GroupMap {
 
 #ifdef __CUDACC__
 // relative target index (0 .. count-1) of member m of patch grp, or -1
-__device__ __forceinline__ long long group_member(const GroupMap& gm, const TargetsDev& tg, long long grp, int m) {
+__device__ __forceinline__ long long group_member(const GroupMap& gm, const TargetsDev& tg, long long grp, int m,
+                                                  int* ci = nullptr) {
+  if (ci) ci[0] = ci[1] = ci[2] = 0;
   if (grp >= gm.ngroups) return -1;
   if (gm.sx == 8) {
     const long long tt = grp * 8 + m;
@@ -55,6 +59,11 @@ __device__ __forceinline__ long long group_member(const GroupMap& gm, const Targ
     z = (r / gm.nyb + gm.zb0) * gm.sz + l;
   }
   if (x >= gm.nx || y >= gm.ny || z >= gm.nz) return -1;
+  if (ci) {
+    ci[0] = (int)x;
+    ci[1] = (int)y;
+    ci[2] = (int)z;
+  }
   const long long tt = x + gm.nx * (y + gm.ny * z) - tg.first;
   return (tt >= 0 && tt < tg.count) ? tt : -1;
 }

@@ -45,8 +45,9 @@ job_index_kernel(TargetsDev tg, GroupMap gm, int k, int kmax, int smax, int minn
   // members of the patch: lanes 0..7
   long long tt = -1;
   int n = 0, fl = 0;
+  int ci[3] = {0, 0, 0};
   if (lane < 8) {
-    tt = group_member(gm, tg, grp, lane);
+    tt = group_member(gm, tg, grp, lane, ci);
     if (tt >= 0) {
       n = cnt[tt];
       fl = 1;
@@ -107,13 +108,15 @@ job_index_kernel(TargetsDev tg, GroupMap gm, int k, int kmax, int smax, int minn
     J.n[lane] = (unsigned char)n;
     J.fl[lane] = (unsigned char)fl;
     J.tt[lane] = (int)tt;
+    J.ci[lane][0] = ci[0];
+    J.ci[lane][1] = ci[1];
+    J.ci[lane][2] = ci[2];
   }
   if (P > GSM_JOB_PMAX) {   // the union does not fit the pool: the solve kernel assembles this job directly
     if (lane == 0) {
       J.P = -1;
       J.S = 0;
     }
-    if (lane < 8) J.mask[lane] = 0ull;
     return;
   }
   // rank the pool: samples common to every active member first, then ascending record position
@@ -152,21 +155,25 @@ job_index_kernel(TargetsDev tg, GroupMap gm, int k, int kmax, int smax, int minn
     J.P = P;
     J.S = nactive > 0 ? min(smax, c >> 3) : 0;
   }
-  // membership masks
-  unsigned long long mymask = 0ull;
+  // slot order of every member: ascending pool rank, i.e. an entry of rank r sits in slot popc(mask below r)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     unsigned lo = 0u, hi = 0u;
+    int r = -1;
     if (key8[i] >= 0) {
-      const int r = W.urank[W.hval[hs8[i]] & 255];
+      r = W.urank[W.hval[hs8[i]] & 255];
       if (r < 32) lo = 1u << r;
       else hi = 1u << (r - 32);
     }
     lo = __reduce_or_sync(0xffffffffu, lo);
     hi = __reduce_or_sync(0xffffffffu, hi);
-    if (lane == i) mymask = ((unsigned long long)hi << 32) | lo;
+    const int nn = __popc(lo) + __popc(hi);
+    if (r >= 0) {
+      const int slot = r < 32 ? __popc(lo & ((1u << r) - 1u)) : __popc(lo) + __popc(hi & ((1u << (r - 32)) - 1u));
+      J.sid[i][slot] = (unsigned char)r;
+    }
+    if (lane >= nn) J.sid[i][lane] = 255;
   }
-  if (lane < 8) J.mask[lane] = mymask;
 }
 
 }  // namespace

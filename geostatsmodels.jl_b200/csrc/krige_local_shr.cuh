@@ -205,7 +205,6 @@ struct alignas(128) ShrSmem {
   double4 prec[NBJ][PMAX];                              // pooled records {x, y, z, value} by rank
   double fW[NBJ][3][64];                                // inverse diagonal factors of the shared columns
   double fL[NBJ][3][64];                                // shared blocks (1,0), (2,0), (2,1)
-  int sids[2][SW][32];                                  // pool rank of every slot (-1: empty)
   int hbad[NBH][4];                                     // shared diagonal block not positive definite
   int flag[2][SW];                                      // private diagonal-block failures, by job parity
 };
@@ -269,6 +268,18 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     return make_double2(r == c0 ? v.sill : e0, r == c1 ? v.sill : e1);
   };
   auto stage_on = [&](int q, int s) -> bool { return q >= 0 && q < niter && S.J[q & (NBH - 1)].S > s; };
+  // coordinates of member w's target of a job: grid index from the descriptor (same rounding as
+  // gsm_target_coords: (origin + i * spacing) + spacing / 2, every operation rounded once)
+  auto target_xyz = [&](const JobIdx& Jq, int w, double& x, double& y, double& z) {
+    if (tg.kind == GSM_TARGETS_GRID) {
+      x = __dadd_rn(__dadd_rn(tg.origin[0], __dmul_rn((double)Jq.ci[w][0], tg.spacing[0])), __dmul_rn(tg.spacing[0], 0.5));
+      y = __dadd_rn(__dadd_rn(tg.origin[1], __dmul_rn((double)Jq.ci[w][1], tg.spacing[1])), __dmul_rn(tg.spacing[1], 0.5));
+      z = __dadd_rn(__dadd_rn(tg.origin[2], __dmul_rn((double)Jq.ci[w][2], tg.spacing[2])), __dmul_rn(tg.spacing[2], 0.5));
+    } else {
+      x = y = z = 0.0;
+      if (Jq.tt[w] >= 0) gsm_target_coords(tg, tg.first + Jq.tt[w], x, y, z);
+    }
+  };
 
   if (warp == WD) {
     // ---------------- diagonal-block warp ----------------
@@ -328,7 +339,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
               gq[p] -= (m.exps[p][0] == 0 && m.exps[p][1] == 0 && m.exps[p][2] == 0) ? 1.0 : 0.0;
           } else {
             double tx, ty, tz;
-            gsm_target_coords(tg, tg.first + tt, tx, ty, tz);
+            target_xyz(Jj, lane, tx, ty, tz);
 #pragma unroll
             for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, tx, ty, tz);
           }
@@ -421,8 +432,8 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     else
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
   };
-  auto L0 = [&](int q) __attribute__((always_inline)) {   // descriptor: one int per lane of warps 0..2
-    if (warp < 3) {
+  auto L0 = [&](int q) __attribute__((always_inline)) {   // descriptor: one int per lane of warps 0..5
+    if (warp < GSM_JOB_WORDS / 32) {
       int* dst = reinterpret_cast<int*>(&S.J[q & (NBH - 1)]) + warp * 32 + lane;
       if (q < niter)
         cp_async(dst, reinterpret_cast<const int*>(&jobs[blockIdx.x + (long long)q * gridDim.x]) + warp * 32 + lane,
@@ -430,7 +441,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       else
         *dst = 0;   // past the end: an empty descriptor
     }
-    if (warp == 3 && lane < 4) S.hbad[q & (NBH - 1)][lane] = 0;
+    if (warp == 6 && lane < 4) S.hbad[q & (NBH - 1)][lane] = 0;
   };
   auto R0 = [&](int q) __attribute__((always_inline)) {   // pooled record of rank warp*32+lane (warps 0, 1)
     if (warp < 2 && q < niter) {
@@ -457,16 +468,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     const bool live = lane < n;
     double rx = 0.0, ry = 0.0, rz = 0.0, rw = 0.0;
     if (Jq.P >= 0) {
-      // slot l holds the pooled sample whose rank is the l-th set bit of the member's mask: every set bit
-      // r scatters itself to slot popc(mask below r)
-      const unsigned long long mk = Jq.mask[warp];
-      const unsigned lo = (unsigned)mk, hi = (unsigned)(mk >> 32);
-      S.sids[bf][warp][lane] = -1;
-      __syncwarp();
-      if ((lo >> lane) & 1u) S.sids[bf][warp][__popc(lo & ((1u << lane) - 1u))] = lane;
-      if ((hi >> lane) & 1u) S.sids[bf][warp][__popc(lo) + __popc(hi & ((1u << lane) - 1u))] = 32 + lane;
-      __syncwarp();
-      const int id = S.sids[bf][warp][lane];
+      const int id = Jq.sid[warp][lane];   // slot order from the descriptor (255: empty)
       if (live) {
         const double2 xy = *reinterpret_cast<const double2*>(&S.prec[qb][id]);
         const double2 zw = *reinterpret_cast<const double2*>(&S.prec[qb][id].z);
@@ -486,8 +488,8 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       S.py[bf][warp][lane] = ry;
       if (DIM3) S.pz[bf][warp][lane] = rz;
     }
-    double x_tx = 0.0, x_ty = 0.0, x_tz = 0.0;
-    if (tt >= 0) gsm_target_coords(tg, tg.first + tt, x_tx, x_ty, x_tz);
+    double x_tx, x_ty, x_tz;
+    target_xyz(Jq, warp, x_tx, x_ty, x_tz);
     const double dx = rx - x_tx, dy = ry - x_ty, dz = DIM3 ? rz - x_tz : 0.0;
     const double d2t = DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx);
     S.rhs[bf][warp][0][lane] = live ? cov_fast(cf, d2t) : 0.0;
@@ -672,9 +674,11 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     if (real) {
 #pragma unroll
       for (int I = 0; I < NBC; ++I) {
-        irow[I] = S.sids[buf][warp][8 * I + g];
+        const int ir = Jj.sid[warp][8 * I + g];
+        const uchar2 ic = *reinterpret_cast<const uchar2*>(&Jj.sid[warp][8 * I + 2 * t]);
+        irow[I] = ir == 255 ? -1 : ir;
         rbase[I] = irow[I] * PLD;
-        icol[I] = *reinterpret_cast<const int2*>(&S.sids[buf][warp][8 * I + 2 * t]);
+        icol[I] = make_int2(ic.x == 255 ? -1 : (int)ic.x, ic.y == 255 ? -1 : (int)ic.y);
       }
 #pragma unroll
       for (int r = 0; r < NRB; ++r)
