@@ -517,7 +517,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     const int P = Jq.P, S8 = 8 * Jq.S;
     const int total = (P - S8) * P;    // (negative for overflow jobs: nothing to do)
     const float invP = 1.0f / (float)max(P, 1);
-#pragma unroll 2
+#pragma unroll 1
     for (int e = warp * 32 + lane; e < total; e += NSYS) {
       const int rr = (int)(((float)e + 0.5f) * invP);
       const int bc = e - rr * P;
