@@ -78,7 +78,7 @@ struct CovFast {
   int kind;
   double sill, c1, k1, k2, inv_r, inv_r2, cs, range2, cfar;
 };
-__device__ __forceinline__ CovFast make_cov(const VarioDev& v) {
+__host__ __device__ __forceinline__ CovFast make_cov(const VarioDev& v) {
   CovFast c;
   c.kind = v.kind;
   c.sill = v.sill;
@@ -214,7 +214,8 @@ template <int NCON, bool DIM3, int NBC>
 __global__ void __launch_bounds__(NTH, (2 + NCON > 8) ? 1 : 2)
 local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant__ VarioDev v,
                        const __grid_constant__ ModelDev m, const __grid_constant__ TargetsDev tg,
-                       const JobIdx* __restrict__ jobs, long long ngroups, int k, int centered,
+                       const __grid_constant__ CovFast cf, const JobIdx* __restrict__ jobs, long long ngroups, int k,
+                       int centered,
                        const int* __restrict__ pos, double* __restrict__ out_mean, double* __restrict__ out_var,
                        unsigned char* __restrict__ out_status) {
   constexpr int NR = 2 + NCON;
@@ -238,7 +239,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
   for (int e = threadIdx.x; e < NBH * 4; e += NTH) (&S.hbad[0][0])[e] = 0;
   __syncthreads();
 
-  const CovFast cf = make_cov(v);
+  // (cf: the covariance constants, a kernel parameter so they are constant-bank operands, not 20 live registers)
   // X <- X W'  (panel solve); two independent accumulators so the two k-chunks overlap
   auto panel = [&](double2& X, const double2& W) {
     double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
@@ -757,7 +758,8 @@ int launch_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const Targets
   const int blocks = (int)std::min<long long>(ngroups, 148LL * per_sm);
   auto kern = local_krige_shr_kernel<NCON, DIM3, NBC>;
   GSM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, NTH, smem, ctx->stream>>>(ctx->bins, v, m, tg, jobs, ngroups, k, centered, pos, mean, var, status);
+  kern<<<blocks, NTH, smem, ctx->stream>>>(ctx->bins, v, m, tg, make_cov(v), jobs, ngroups, k, centered, pos, mean, var,
+                                           status);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
   return GSM_OK;

@@ -524,3 +524,22 @@ def test_shared_factor_kernel_steady_state(gsm, oracle, kind, dim, deg, k, dims,
     gmu, gvar = np.ma.filled(got.mu, 0.0), np.ma.filled(got.sigma, 0.0)
     assert np.allclose(gmu[ok], mu[ok], rtol=rtol, atol=1e-9 if deg else ATOL), np.abs(gmu[ok] - mu[ok]).max()
     assert np.allclose(gvar[ok], var[ok], rtol=rtol, atol=1e-9 if deg else ATOL), np.abs(gvar[ok] - var[ok]).max()
+
+
+@pytest.mark.parametrize("dims,k", [((3, 2), 12), ((5, 1), 16), ((1, 9), 10), ((2, 2, 2), 20), ((7, 3, 1), 32),
+                                    ((9, 5, 3), 32), ((4, 2), 32), ((33, 17), 9)])
+def test_shared_factor_kernel_tiny_and_degenerate_grids(gsm, oracle, dims, k):
+    """Grids smaller than / not aligned with the 4 x 2 and 2 x 2 x 2 patches, fewer jobs than CTAs."""
+    o = oracle
+    dim = len(dims)
+    rng = np.random.default_rng(5 + sum(dims) + k)
+    X = rng.uniform(0, 10, size=(400, dim))
+    z = rng.standard_normal(400)
+    vario = o.Variogram(o.SPHERICAL, 1.0, 0.1, 4.0)
+    og = o.Grid(tuple(0.0 for _ in dims), tuple(10.0 / d for d in dims), dims)
+    mu, var, st = o.fitpredict(o.ordinary_kriging(vario), X, z, og, maxneighbors=k, prob=True)
+    gm = gsm.OrdinaryKriging(gsm.SphericalVariogram(sill=1.0, range=4.0, nugget=0.1))
+    grid = gsm.CartesianGrid(tuple(0.0 for _ in dims), tuple(10.0 for _ in dims), dims=dims)
+    got = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=k, prob=True).z
+    assert (st == 0).all()
+    assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL) and np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL)
