@@ -224,6 +224,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
   constexpr int NROWS = NBC + NRB;          // block rows of the augmented matrix
   constexpr int KMAX = 8 * NBC;             // neighbour slots
   constexpr int SMAX = NBC - 1;             // shared block columns at most (the last column stays private)
+  constexpr int S2SPEC = (DIM3 && SMAX >= 2) ? SMAX - 1 : -1;   // second specialised job shape (3-D patches share less)
   static_assert(NR <= 16 && NBC >= 1 && NBC <= 4, "unsupported shape");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ShrSmem<NR>& S = *reinterpret_cast<ShrSmem<NR>*>(smem_raw);
@@ -516,22 +517,51 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     const int qb = q & (NBJ - 1);
     const JobIdx& Jq = S.J[q & (NBH - 1)];
     const int P = Jq.P, S8 = 8 * Jq.S;
-    const int total = (P - S8) * P;    // (negative for overflow jobs: nothing to do)
-    const float invP = 1.0f / (float)max(P, 1);
+    const double4* pr = S.prec[qb];
+    if (!DIM3) {
+      // 2-D patches (P - S8 ~ 14 rows): the full rows of the non-shared samples, 2-3 evaluations per thread;
+      // exploiting the symmetry costs more index arithmetic than it saves here (measured)
+      const int total = (P - S8) * P;    // (negative for overflow jobs: nothing to do)
+      const float invP = 1.0f / (float)max(P, 1);
 #pragma unroll 1
-    for (int e = warp * 32 + lane; e < total; e += NSYS) {
-      const int rr = (int)(((float)e + 0.5f) * invP);
-      const int bc = e - rr * P;
-      const int a = S8 + rr;
-      double val = v.sill;
-      if (a != bc) {
-        const double2 axy = *reinterpret_cast<const double2*>(&S.prec[qb][a]);
-        const double2 bxy = *reinterpret_cast<const double2*>(&S.prec[qb][bc]);
-        const double dx = axy.x - bxy.x, dy = axy.y - bxy.y;
-        const double dz = DIM3 ? S.prec[qb][a].z - S.prec[qb][bc].z : 0.0;
-        val = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
+      for (int e = warp * 32 + lane; e < total; e += NSYS) {
+        const int rr = (int)(((float)e + 0.5f) * invP);
+        const int bc = e - rr * P;
+        const int a = S8 + rr;
+        double val = v.sill;
+        if (a != bc) {
+          const double2 axy = *reinterpret_cast<const double2*>(&pr[a]);
+          const double2 bxy = *reinterpret_cast<const double2*>(&pr[bc]);
+          const double dx = axy.x - bxy.x, dy = axy.y - bxy.y;
+          val = cov_fast(cf, fma(dy, dy, dx * dx));
+        }
+        S.PC[a * PLD + bc] = val;
       }
-      S.PC[a * PLD + bc] = val;
+    } else {
+      // 3-D patches share less (P - S8 ~ 32 rows): columns b <= a only, the rest by symmetry.  Row a' = a - S8 has
+      // S8 + a' + 1 entries; pairing row a' with row Pp-1-a' gives rows of constant width W, so (a, b) follows
+      // from one float multiply.
+      const int Pp = P - S8, W = 2 * S8 + Pp + 1, total = ((Pp + 1) >> 1) * W;
+      const float invW = 1.0f / (float)W;
+#pragma unroll 1
+      for (int e = warp * 32 + lane; e < total; e += NSYS) {
+        const int rr = (int)(((float)e + 0.5f) * invW);
+        const int cc = e - rr * W;
+        const bool first = cc <= S8 + rr;
+        const int ap = first ? rr : Pp - 1 - rr;
+        const int bc = first ? cc : cc - (S8 + rr + 1);
+        if (!first && ap == rr) continue;   // odd Pp: the middle row is its own partner
+        const int a = S8 + ap;
+        double val = v.sill;
+        if (a != bc) {
+          const double2 axy = *reinterpret_cast<const double2*>(&pr[a]);
+          const double2 bxy = *reinterpret_cast<const double2*>(&pr[bc]);
+          const double dx = axy.x - bxy.x, dy = axy.y - bxy.y, dz = pr[a].z - pr[bc].z;
+          val = cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+        }
+        S.PC[a * PLD + bc] = val;
+        if (bc >= S8) S.PC[bc * PLD + a] = val;
+      }
     }
   };
   // Shared-factor pipeline, system-warp side, run after the last round of job j:
@@ -687,10 +717,14 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         for (int q = 0; q < NRB; ++q) Gb[r][q] = make_double2(0.0, 0.0);
       // every slot live and pooled (the common case): plain indexed loads, no calls on this path
       using SFull = std::integral_constant<int, SMAX>;
+      using SNext = std::integral_constant<int, (S2SPEC >= 0 ? S2SPEC : 0)>;
       using SAny = std::integral_constant<int, -1>;
       if (fastg && SMAX > 0 && S_ == SMAX) {   // the common case, fully specialised: straight-line code
 #pragma unroll
         for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{}, SFull{});
+      } else if (fastg && S2SPEC >= 0 && S_ == S2SPEC) {   // the common case of 2 x 2 x 2 patches
+#pragma unroll
+        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{}, SNext{});
       } else if (fastg) {
         if (S_ == 0) post(gath(0, 0, std::true_type{}));
 #pragma unroll
@@ -716,10 +750,14 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
 
     if (real) {
       using SFull = std::integral_constant<int, SMAX>;
+      using SNext = std::integral_constant<int, (S2SPEC >= 0 ? S2SPEC : 0)>;
       using SAny = std::integral_constant<int, -1>;
       if (fastg && SMAX > 0 && S_ == SMAX) {
 #pragma unroll
         for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::true_type{}, SFull{});
+      } else if (fastg && S2SPEC >= 0 && S_ == S2SPEC) {
+#pragma unroll
+        for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::true_type{}, SNext{});
       } else if (fastg) {
 #pragma unroll
         for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::true_type{}, SAny{});
