@@ -338,9 +338,9 @@ def run_ours(args):
                                         " MEASURED_PEAKS.json has no FP64 entry" % (fp64_dfma, fp64_dmma),
                          "flops_per_prediction": fpp, "launch_ms": solve_launch_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 systems) from the
-                         # `ncu --set full` capture summarised in profiles/r01_local_krige_shr_ncu_summary.txt;
-                         # algorithmic: 2^17 job descriptors x 384 B + 2^20 x 17 B of outputs = 68 MB
-                         "traffic": 53.8e6, "traffic_unit": "bytes per launch (ncu; the descriptors are still L2-resident)",
+                         # `ncu --set full` capture summarised in profiles/r01_knn_index_local_krige_shr_ncu_summary.txt;
+                         # algorithmic: 2^17 job descriptors x 768 B + 2^20 x 17 B of outputs = 118.5 MB
+                         "traffic": 115.9e6, "traffic_unit": "bytes per launch (ncu)",
                          "algorithmic_flops_per_launch": fpp * min(M, 1 << 20),
                          "bound_note": "FP64 pipe; on B200 the DMMA (tensor) and DFMA paths are one pipe "
                                        "(tools/pipebench.cu), so the peak is the larger of the two measured rates",
