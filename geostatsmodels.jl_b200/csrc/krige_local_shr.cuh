@@ -25,7 +25,10 @@
 #include "gsm_internal.cuh"
 #include "krige_local_jobs.cuh"
 
-#if defined(GSM_TRACE) && GSM_SHR_DIM3 == 0 && GSM_SHR_NBC == 4   // developer phase trace: 2-D, k <= 32 unit only
+#ifndef GSM_TRACE_DIM3
+#define GSM_TRACE_DIM3 0
+#endif
+#if defined(GSM_TRACE) && GSM_SHR_DIM3 == GSM_TRACE_DIM3 && GSM_SHR_NBC == 4   // developer phase trace: one unit only (k <= 32; 2-D unless GSM_TRACE_DIM3=1)
 __device__ long long* g_trace3 = nullptr;
 extern "C" __attribute__((visibility("default"))) int gsm_debug_set_trace3(long long* p) {
   return cudaMemcpyToSymbol(g_trace3, &p, sizeof(p)) == cudaSuccess ? 0 : 1;
@@ -624,6 +627,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     const int S_ = real ? Jj.S : 0;
     const int n = real ? Jj.n[warp] : 0;
     const bool pooled = real ? Jj.P >= 0 : true;
+    bool q1_done = false;
     TR(0);
     L0(ji + 5);
     if (ji + 4 >= 0) R0(ji + 4);
@@ -723,8 +727,16 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
 #pragma unroll
         for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{}, SFull{});
       } else if (fastg && S2SPEC >= 0 && S_ == S2SPEC) {   // the common case of 2 x 2 x 2 patches
+        // two hand-offs: the next job's right-hand sides (Q1) fill the first wait, its pooled covariances
+        // (which must follow this job's last gather from PC) the second
 #pragma unroll
-        for (int kb = 0; kb <= KREL; ++kb) column(kb, std::true_type{}, SNext{});
+        for (int kb = 0; kb <= KREL; ++kb) {
+          column(kb, std::true_type{}, SNext{});
+          if (NRB == 1 && kb == S2SPEC - 1 && kb < KREL) {   // (measured slower with 16 right-hand-side rows)
+            if (ji + 1 < niter) Q1(ji + 1, buf ^ 1);
+            q1_done = true;
+          }
+        }
       } else if (fastg) {
         if (S_ == 0) post(gath(0, 0, std::true_type{}));
 #pragma unroll
@@ -742,7 +754,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     LR1();
     TR(4);
     if (ji + 1 >= 0 && ji + 1 < niter) {
-      Q1(ji + 1, buf ^ 1);
+      if (!q1_done) Q1(ji + 1, buf ^ 1);
       TR(5);
       Q4(ji + 1);
     }
