@@ -76,7 +76,7 @@ __device__ __forceinline__ void sift_up(Heap& hp, int i, double d, int p, const 
 }
 
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long row0, int ntx,
+knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long row0, int ntx, int nty,
            int* __restrict__ out_pos, int* __restrict__ out_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Heap hp;
@@ -92,15 +92,24 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
 
   // Thread -> target map.  Grid targets: a warp covers an 8 x 4 patch of the grid (CTA = 16 x 8), so its
   // lanes sit in the same one or two cells, walk the same rings and turn candidate loads into broadcasts.
-  // Point targets: consecutive indices.
+  // 3-D grids spanning several planes: a 4 x 4 x 2 brick per warp (tiled == 2).  Point targets: consecutive indices.
   long long t0;
-  if (tiled) {
+  if (tiled == 1) {
     const int tid = threadIdx.x, lx = tid & 7, ly = (tid >> 3) & 3, wq = tid >> 5;
     const long long bx = blockIdx.x % ntx, by = blockIdx.x / ntx;
     const long long x = bx * 16 + (wq & 1) * 8 + lx;
     const long long row = row0 + by * 8 + (wq >> 1) * 4 + ly;
     const long long lin = row * tg.dims[0] + x;
     t0 = (x < tg.dims[0] && lin >= tg.first) ? lin - tg.first : tg.count;   // out of range -> skipped below
+  } else if (tiled == 2) {
+    // 3-D grids: a warp covers a 4 x 4 x 2 brick (CTA = 8 x 8 x 2); row0 is the first plane pair of the slab
+    const int tid = threadIdx.x, ln = tid & 31, wq = tid >> 5;
+    const int lx = ln & 3, ly = (ln >> 2) & 3, lz = ln >> 4;
+    const long long bx = blockIdx.x % ntx, r = blockIdx.x / ntx, by = r % nty, bz = r / nty;
+    const long long x = bx * 8 + (wq & 1) * 4 + lx, y = by * 8 + (wq >> 1) * 4 + ly, z = (row0 + bz) * 2 + lz;
+    const long long lin = x + tg.dims[0] * (y + tg.dims[1] * z);
+    const bool in = x < tg.dims[0] && y < tg.dims[1] && z < tg.dims[2] && lin >= tg.first && lin < tg.first + tg.count;
+    t0 = in ? lin - tg.first : tg.count;
   } else {
     t0 = (blockIdx.x * (long long)KNN_THREADS + threadIdx.x) * KNN_RUN;
   }
@@ -303,14 +312,23 @@ int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int
   long long blocks = (tg.count + (long long)KNN_THREADS * KNN_RUN - 1) / ((long long)KNN_THREADS * KNN_RUN);
   int tiled = 0, ntx = 1;
   long long row0 = 0;
+  int nty = 1;
   if (tg.kind == GSM_TARGETS_GRID && KNN_RUN == 1 && tg.dims[0] >= 8) {
     tiled = 1;
     row0 = tg.first / tg.dims[0];
     const long long rlast = (tg.first + tg.count - 1) / tg.dims[0];
     ntx = (int)((tg.dims[0] + 15) / 16);
     blocks = (long long)ntx * ((rlast - row0 + 1 + 7) / 8);
+    const long long z_lo = row0 / tg.dims[1], z_hi = rlast / tg.dims[1];
+    if (tg.dim >= 3 && tg.dims[2] > 1 && z_hi > z_lo && tg.dims[1] >= 4) {   // bricks pay once the slab spans planes
+      tiled = 2;
+      row0 = z_lo / 2;
+      ntx = (int)((tg.dims[0] + 7) / 8);
+      nty = (int)((tg.dims[1] + 7) / 8);
+      blocks = (long long)ntx * nty * (z_hi / 2 - row0 + 1);
+    }
   }
-  knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, tiled, row0, ntx, d_pos,
+  knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, tiled, row0, ntx, nty, d_pos,
                                                                   d_cnt);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
