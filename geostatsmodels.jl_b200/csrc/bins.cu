@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "gsm_internal.cuh"
 
 namespace {
@@ -119,7 +121,10 @@ __global__ void sort_cells_kernel(int ncells, const int* __restrict__ cell_start
 }  // namespace
 
 // Average samples per cell the bins aim for.  Tuned on B200 (kNN kernel).
-static double target_occupancy(int dim) { return dim >= 3 ? 1.5 : 2.0; }
+static double target_occupancy(int dim) {
+  if (const char* e = getenv("GSM_BIN_OCCUPANCY")) return atof(e);   // developer switch (tuning)
+  return dim >= 3 ? 2.2 : 2.0;
+}
 
 int gsm_build_bins(gsm_ctx* ctx) {
   const int dim = ctx->dim;
