@@ -285,7 +285,7 @@ int gsm_destroy(gsm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->coords, &ctx->values, &ctx->rec, &ctx->sidx, &ctx->cell_of, &ctx->cell_start,
-                    &ctx->cell_fill, &ctx->cub_tmp, &ctx->red, &ctx->nbr_pos, &ctx->nbr_cnt, &ctx->job_idx, &ctx->summ_dev, &ctx->out_mean,
+                    &ctx->cell_fill, &ctx->cub_tmp, &ctx->red, &ctx->nbr_pos, &ctx->nbr_cnt, &ctx->job_idx, &ctx->summ_dev, &ctx->glob_R, &ctx->glob_acc, &ctx->out_mean,
                     &ctx->out_var, &ctx->out_status, &ctx->out_nbr, &ctx->tgt_points};
   for (DevBuf* b : bufs) free_buf(*b);
   cudaStreamDestroy(ctx->stream);

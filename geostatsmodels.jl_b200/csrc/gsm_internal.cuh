@@ -105,6 +105,7 @@ struct gsm_ctx {
   DevBuf nbr_cnt;     // chunk int
   DevBuf job_idx;     // job descriptors of the shared-factor local-Kriging kernel
   DevBuf summ_dev;    // 4 x u64 status counters of the current call
+  DevBuf glob_R, glob_acc;   // global Kriging prediction: covariance tile of a target batch, per-target sums
   DevBuf out_mean, out_var, out_status, out_nbr, tgt_points;
 
   // events for gsm_timings

@@ -16,6 +16,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+#include <string>
+
 #include "gsm_internal.cuh"
 
 namespace {
@@ -342,6 +345,176 @@ __global__ void __launch_bounds__(PTHREADS) global_predict_kernel(GlobalDev gd, 
     if (out_var) out_var[t0 + tid] = var + 1e-10;
   }
 }
+
+// ---- batched prediction (default): covariance tile once, then a triangular DMMA GEMM with a norm epilogue ----
+// For a batch of Mb targets:
+//   1. global_r_kernel     R[k][n] = cov(sample k, target n), k-major (np x Mb), written once; and the inner
+//                          products dots[c][n] = sum_k D[c][k] R[k][n] (mean and drift terms).
+//   2. global_gemm_norm    Y = Linv R is never stored: each CTA forms a 128 x 64 block of it on the DMMA path
+//                          (3-stage cp.async pipeline, Linv lower triangular so K stops at the block's last row)
+//                          and adds the column sums of squares to uu[n] = |Linv c0(n)|^2 = c0' C^-1 c0.
+//   3. global_finish       mean, variance and the drift correction per target.
+// The first version (global_predict_kernel above) rebuilt the covariance tile for every row block (16x redundant
+// at N = 4000) and had no load / compute overlap; it is kept as GSM_GLOBAL_IMPL=v1.
+constexpr int QK = 16;            // k step
+constexpr int QLDA = PM + 4;      // As[k][m]: stride = 4 mod 16 doubles -> the (t, g) fragment loads are conflict-free
+constexpr int QLDB = PT + 4;      // Bs[k][n]
+constexpr int QSTAGES = 3;
+constexpr int QTHREADS = 256;
+
+__global__ void __launch_bounds__(256)
+global_r_kernel(GlobalDev gd, VarioDev v, TargetsDev tg, long long t0, int mb, double* __restrict__ R,
+                double* __restrict__ dots) {
+  // block: 64 targets x 128 samples; thread: target tid % 64, 32 samples of group tid / 64
+  __shared__ double part[4][1 + GSM_MAX_DRIFT][64];
+  const int tid = threadIdx.x, nl = tid & 63, grp = tid >> 6;
+  const int n = blockIdx.x * 64 + nl;
+  const int k0 = blockIdx.y * 128 + grp * 32;
+  double tx = 0, ty = 0, tz = 0;
+  const bool tlive = t0 + n < tg.count;
+  if (tlive) gsm_target_coords(tg, tg.first + t0 + n, tx, ty, tz);
+  double acc[1 + GSM_MAX_DRIFT];
+  for (int c = 0; c <= gd.ncon; ++c) acc[c] = 0.0;
+  for (int kk = 0; kk < 32; ++kk) {
+    const int s = k0 + kk;
+    double r = 0.0;
+    if (s < gd.n && tlive) {
+      const double dx = gd.px[s] - tx, dy = gd.py[s] - ty, dz = gd.pz[s] - tz;
+      r = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+      for (int c = 0; c <= gd.ncon; ++c) acc[c] = fma(gd.D[(size_t)c * gd.np + s], r, acc[c]);
+    }
+    R[(size_t)s * mb + n] = r;
+  }
+  for (int c = 0; c <= gd.ncon; ++c) part[grp][c][nl] = acc[c];
+  __syncthreads();
+  // partial sums of this sample block; global_finish_kernel adds the blocks in a fixed order (reproducible)
+  if (grp == 0)
+    for (int c = 0; c <= gd.ncon; ++c)
+      dots[((size_t)blockIdx.y * (1 + GSM_MAX_DRIFT) + c) * mb + n] =
+          (part[0][c][nl] + part[1][c][nl]) + (part[2][c][nl] + part[3][c][nl]);
+}
+
+__global__ void __launch_bounds__(QTHREADS, 2)
+global_gemm_norm_kernel(const double* __restrict__ Linv, int np, const double* __restrict__ R, int mb, int ncb,
+                        double* __restrict__ uu) {
+  extern __shared__ __align__(16) double gsm_smem[];
+  double* As = gsm_smem;                              // [QSTAGES][QK][QLDA]
+  double* Bs = gsm_smem + QSTAGES * QK * QLDA;        // [QSTAGES][QK][QLDB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int nib = np / PM;
+  // heavy row blocks (long K) first
+  const int ib = nib - 1 - (int)(blockIdx.x / ncb), cb = (int)(blockIdx.x % ncb);
+  const int ksteps = (ib + 1) * PM / QK;
+  const double* Ag = Linv + (size_t)ib * PM;          // + k * np + m
+  const double* Bg = R + (size_t)cb * PT;             // + k * mb + n
+
+  auto load_stage = [&](int st, int ks) {
+    const int k0 = ks * QK;
+    // A: QK x 128 doubles = 1024 16-byte chunks, 4 per thread; B: QK x 64 doubles = 512 chunks, 2 per thread
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ch = tid + q * QTHREADS, k = ch >> 6, m2 = (ch & 63) * 2;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(&As[(st * QK + k) * QLDA + m2]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Ag + (size_t)(k0 + k) * np + m2) : "memory");
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int ch = tid + q * QTHREADS, k = ch >> 5, n2 = (ch & 31) * 2;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(&Bs[(st * QK + k) * QLDB + n2]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Bg + (size_t)(k0 + k) * mb + n2) : "memory");
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < QSTAGES - 1; ++s) {
+    if (s < ksteps) load_stage(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int ks = 0; ks < ksteps; ++ks) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(QSTAGES - 2) : "memory");
+    __syncthreads();   // stage ks landed for everyone; stage ks-1 (about to be refilled) is no longer read
+    if (ks + QSTAGES - 1 < ksteps) load_stage((ks + QSTAGES - 1) % QSTAGES, ks + QSTAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* a = &As[(ks % QSTAGES) * QK * QLDA];
+    const double* b = &Bs[(ks % QSTAGES) * QK * QLDB];
+#pragma unroll
+    for (int kk = 0; kk < QK; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = a[(kk + t) * QLDA + wm + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = b[(kk + t) * QLDB + wn + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  // column sums of squares of this 128 x 64 block of Y: one partial per (row block, column), fixed order
+  __syncthreads();                       // the tile buffers are free: reuse them for the 4 x 64 warp-row partials
+  double* red = gsm_smem;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      double p = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p = fma(acc[i][j][s], acc[i][j][s], p);
+      p += __shfl_xor_sync(0xffffffffu, p, 4);
+      p += __shfl_xor_sync(0xffffffffu, p, 8);
+      p += __shfl_xor_sync(0xffffffffu, p, 16);
+      if (g == 0) red[(warp & 3) * PT + wn + j * 8 + 2 * t + s] = p;
+    }
+  __syncthreads();
+  if (tid < PT) uu[(size_t)ib * mb + cb * PT + tid] = (red[tid] + red[PT + tid]) + (red[2 * PT + tid] + red[3 * PT + tid]);
+}
+
+__global__ void global_finish_kernel(GlobalDev gd, VarioDev v, ModelDev m, TargetsDev tg, long long t0, int mb,
+                                     const double* __restrict__ dots_part, const double* __restrict__ uu_part,
+                                     double* __restrict__ out_mean, double* __restrict__ out_var) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= mb || t0 + n >= tg.count) return;
+  const int ncon = gd.ncon, nib = gd.np / PM;
+  double dots[1 + GSM_MAX_DRIFT];
+  double usum = 0.0;
+  for (int c = 0; c <= ncon; ++c) dots[c] = 0.0;
+  for (int ib = 0; ib < nib; ++ib) {
+    for (int c = 0; c <= ncon; ++c) dots[c] += dots_part[((size_t)ib * (1 + GSM_MAX_DRIFT) + c) * mb + n];
+    if (out_var) usum += uu_part[(size_t)ib * mb + n];
+  }
+  double mean = dots[0], var = v.sill - usum;
+  if (m.kind == GSM_KRIG_SIMPLE) {
+    mean += m.mean;
+  } else {
+    double tx, ty, tz;
+    gsm_target_coords(tg, tg.first + t0 + n, tx, ty, tz);
+    double gq[GSM_MAX_DRIFT], nu[GSM_MAX_DRIFT];
+    for (int c = 0; c < ncon; ++c) {
+      const double f0 = (m.kind == GSM_KRIG_ORDINARY) ? 1.0 : gsm_drift(m, c, tx, ty, tz);
+      gq[c] = dots[1 + c] - f0;
+    }
+    for (int c = 0; c < ncon; ++c) {
+      double s = 0.0;
+      for (int d = 0; d < ncon; ++d) s = fma(gd.Ginv[c * ncon + d], gq[d], s);
+      nu[c] = s;
+    }
+    for (int c = 0; c < ncon; ++c) {
+      mean = fma(-gd.hw[c], nu[c], mean);
+      var = fma(gq[c], nu[c], var);
+    }
+  }
+  out_mean[t0 + n] = mean;
+  if (out_var) out_var[t0 + n] = var + 1e-10;
+}
+
 
 __global__ void split_coords_kernel(const double* __restrict__ coords, int dim, int n, int np, double* __restrict__ px,
                                     double* __restrict__ py, double* __restrict__ pz) {
@@ -703,10 +876,34 @@ int gsm_global_krige_predict(gsm_fit* f, const gsm_targets* t, double* out_mean,
     md.ndrift = f->model.kind == GSM_KRIG_UNIVERSAL ? f->model.ndrift : 0;
     for (int a = 0; a < md.ndrift; ++a)
       for (int d = 0; d < 3; ++d) md.exps[a][d] = f->model.exps[a][d];
-    const unsigned blocks = (unsigned)((count + PT - 1) / PT);
-    global_predict_kernel<<<blocks, PTHREADS, 0, st>>>(gd, vd, md, td, dmean, dvar);
-    ctx->tim.launches++;
-    GSM_CUDA(ctx, cudaGetLastError());
+    const char* impl_env = getenv("GSM_GLOBAL_IMPL");
+    if (impl_env && std::string(impl_env) == "v1") {
+      const unsigned blocks = (unsigned)((count + PT - 1) / PT);
+      global_predict_kernel<<<blocks, PTHREADS, 0, st>>>(gd, vd, md, td, dmean, dvar);
+      ctx->tim.launches++;
+      GSM_CUDA(ctx, cudaGetLastError());
+    } else {
+      // batches of mb targets: the covariance tile R (np x mb, k-major) stays around 256 MB
+      long long mb = (256LL << 20) / ((long long)np * 8) / PT * PT;
+      mb = std::max<long long>(PT, std::min<long long>(mb, 8192));
+      mb = std::min<long long>(mb, (count + PT - 1) / PT * PT);
+      const int ncb = (int)(mb / PT), nib = np / PM;
+      GSM_CHECK(gsm_reserve(ctx, ctx->glob_R, (size_t)np * mb * sizeof(double)));
+      GSM_CHECK(gsm_reserve(ctx, ctx->glob_acc, (size_t)nib * (2 + GSM_MAX_DRIFT) * mb * sizeof(double)));
+      double* Rb = (double*)ctx->glob_R.p;
+      double* dots = (double*)ctx->glob_acc.p;           // per sample block: (1 + GSM_MAX_DRIFT) x mb partial sums
+      double* uu = dots + (size_t)nib * (1 + GSM_MAX_DRIFT) * mb;   // per row block: mb partial sums of squares
+      const size_t smem = (size_t)QSTAGES * QK * (QLDA + QLDB) * sizeof(double);
+      GSM_CUDA(ctx, cudaFuncSetAttribute(global_gemm_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      for (long long t0 = 0; t0 < count; t0 += mb) {
+        global_r_kernel<<<dim3((unsigned)ncb, (unsigned)nib), 256, 0, st>>>(gd, vd, td, t0, (int)mb, Rb, dots);
+        if (dvar)
+          global_gemm_norm_kernel<<<(unsigned)(ncb * nib), QTHREADS, smem, st>>>(gd.Linv, np, Rb, (int)mb, ncb, uu);
+        global_finish_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(gd, vd, md, td, t0, (int)mb, dots, uu, dmean, dvar);
+        ctx->tim.launches += dvar ? 3 : 2;
+      }
+      GSM_CUDA(ctx, cudaGetLastError());
+    }
   }
   cudaEventRecord(e2, st);
   if (!mean_dev && count > 0)
