@@ -12,10 +12,19 @@ namespace {
 constexpr int IDW_THREADS = 128;
 constexpr int IDW_TILE = 512;
 
+// 1/d, d > 0 finite: hardware seed + two Newton steps (full double precision, no slow-path branch)
+__device__ __forceinline__ double idw_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  y = fma(y, fma(-d, y, 1.0), y);
+  y = fma(y, fma(-d, y, 1.0), y);
+  return y;
+}
+
 // EXPMODE: 1 -> e == 1, 2 -> e == 2, 3 -> other positive integer, 0 -> real exponent
 template <int EXPMODE>
 __device__ __forceinline__ double idw_weight(double d2, double e, int ei) {
-  if (EXPMODE == 2) return 1.0 / d2;
+  if (EXPMODE == 2) return (d2 > 1e-290 && d2 < 1e290) ? idw_rcp(d2) : 1.0 / d2;
   if (EXPMODE == 1) return 1.0 / sqrt(d2);
   const double d = sqrt(d2);
   if (EXPMODE == 3) {
@@ -26,12 +35,22 @@ __device__ __forceinline__ double idw_weight(double d2, double e, int ei) {
   return 1.0 / pow(d, e);
 }
 
-template <int EXPMODE>
-__global__ void __launch_bounds__(IDW_THREADS)
+// IDW_TPB targets per CTA, IDW_SPLIT threads per target: thread (target, q) takes the samples i = q mod IDW_SPLIT
+// of every tile, so a 256 x 256 grid (config C1) still fills the SMs; the IDW_SPLIT partial sums of a target are
+// added in a fixed order (reproducible).
+constexpr int IDW_TPB = 64;
+constexpr int IDW_SPLIT = 4;
+static_assert(IDW_TPB * IDW_SPLIT == 2 * IDW_THREADS, "thread layout");
+
+template <int EXPMODE, bool DIM3>
+__global__ void __launch_bounds__(IDW_TPB * IDW_SPLIT)
 idw_global_kernel(const double* __restrict__ coords, const double* __restrict__ values, int dim, int n,
                   TargetsDev tg, double e, int ei, double* __restrict__ out) {
   __shared__ __align__(16) double sx[IDW_TILE], sy[IDW_TILE], sz[IDW_TILE], sv[IDW_TILE];
-  const long long t = blockIdx.x * (long long)IDW_THREADS + threadIdx.x;
+  __shared__ double psw[IDW_SPLIT][IDW_TPB], pswz[IDW_SPLIT][IDW_TPB], phv[IDW_SPLIT][IDW_TPB];
+  __shared__ int phit[IDW_SPLIT][IDW_TPB];
+  const int tl = threadIdx.x % IDW_TPB, q = threadIdx.x / IDW_TPB;   // a warp shares q: tile reads stay broadcasts
+  const long long t = blockIdx.x * (long long)IDW_TPB + tl;
   const bool active = t < tg.count;
   double tx = 0, ty = 0, tz = 0;
   if (active) gsm_target_coords(tg, tg.first + t, tx, ty, tz);
@@ -41,7 +60,7 @@ idw_global_kernel(const double* __restrict__ coords, const double* __restrict__ 
   for (int base = 0; base < n; base += IDW_TILE) {
     const int m = min(IDW_TILE, n - base);
     __syncthreads();
-    for (int i = threadIdx.x; i < m; i += IDW_THREADS) {
+    for (int i = threadIdx.x; i < m; i += IDW_TPB * IDW_SPLIT) {
       const double* c = coords + (size_t)(base + i) * dim;
       sx[i] = c[0];
       sy[i] = dim > 1 ? c[1] : 0.0;
@@ -51,9 +70,13 @@ idw_global_kernel(const double* __restrict__ coords, const double* __restrict__ 
     __syncthreads();
     if (active) {
 #pragma unroll 4
-      for (int i = 0; i < m; ++i) {
-        const double dx = tx - sx[i], dy = ty - sy[i], dz = tz - sz[i];
-        const double d2 = dx * dx + dy * dy + dz * dz;
+      for (int i = q; i < m; i += IDW_SPLIT) {
+        const double dx = tx - sx[i], dy = ty - sy[i];
+        double d2 = dx * dx + dy * dy;
+        if (DIM3) {
+          const double dz = tz - sz[i];
+          d2 += dz * dz;
+        }
         if (d2 > 0.0) {
           const double w = idw_weight<EXPMODE>(d2, e, ei);
           sw += w;
@@ -65,7 +88,25 @@ idw_global_kernel(const double* __restrict__ coords, const double* __restrict__ 
       }
     }
   }
-  if (active) out[t] = (hit != 0x7fffffff) ? hitv : swz / sw;
+  psw[q][tl] = sw;
+  pswz[q][tl] = swz;
+  phit[q][tl] = hit;
+  phv[q][tl] = hitv;
+  __syncthreads();
+  if (q == 0 && active) {
+    double a = 0.0, bsum = 0.0, hv = 0.0;
+    int h = 0x7fffffff;
+#pragma unroll
+    for (int r = 0; r < IDW_SPLIT; ++r) {
+      a += psw[r][tl];
+      bsum += pswz[r][tl];
+      if (phit[r][tl] < h) {   // the FIRST zero-distance sample (idw.jl:68-69) = the lowest index over the slices
+        h = phit[r][tl];
+        hv = phv[r][tl];
+      }
+    }
+    out[t] = (h != 0x7fffffff) ? hv : bsum / a;
+  }
 }
 
 template <int EXPMODE>
@@ -121,15 +162,23 @@ int gsm_launch_idw_global(gsm_ctx* ctx, double exponent, const TargetsDev& tg, d
   if (tg.count <= 0) return GSM_OK;
   int ei;
   const int mode = exp_mode(exponent, ei);
-  const unsigned blocks = (unsigned)((tg.count + IDW_THREADS - 1) / IDW_THREADS);
+  const unsigned blocks = (unsigned)((tg.count + IDW_TPB - 1) / IDW_TPB);
   const double* c = (const double*)ctx->coords.p;
   const double* v = (const double*)ctx->values.p;
   const int n = (int)ctx->n, dim = ctx->dim;
   switch (mode) {
-    case 1: idw_global_kernel<1><<<blocks, IDW_THREADS, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean); break;
-    case 2: idw_global_kernel<2><<<blocks, IDW_THREADS, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean); break;
-    case 3: idw_global_kernel<3><<<blocks, IDW_THREADS, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean); break;
-    default: idw_global_kernel<0><<<blocks, IDW_THREADS, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean); break;
+    case 1: if (dim > 2) idw_global_kernel<1, true><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      else idw_global_kernel<1, false><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      break;
+    case 2: if (dim > 2) idw_global_kernel<2, true><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      else idw_global_kernel<2, false><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      break;
+    case 3: if (dim > 2) idw_global_kernel<3, true><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      else idw_global_kernel<3, false><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      break;
+    default: if (dim > 2) idw_global_kernel<0, true><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      else idw_global_kernel<0, false><<<blocks, IDW_TPB * IDW_SPLIT, 0, ctx->stream>>>(c, v, dim, n, tg, exponent, ei, d_mean);
+      break;
   }
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
