@@ -149,6 +149,9 @@ int gsm_launch_local_krige_pipe(gsm_ctx* ctx, const VarioDev& v, const ModelDev&
 int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                double* d_mean, double* d_var, unsigned char* d_status);
+int gsm_launch_local_krige_mid(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
+                               const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                               double* d_mean, double* d_var, unsigned char* d_status);
 int gsm_launch_local_krige_big(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                double* d_mean, double* d_var, unsigned char* d_status);

@@ -258,9 +258,18 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool nonconst = false;
   for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
   const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
-  if (k > 32)   // capacity path: one CTA per system, matrix in shared memory
+  if (k > 32) {
+    // 32 < k <= 64: warp-per-system DMMA kernel with the matrix in shared memory (krige_local_mid.cu);
+    // GSM_LOCAL_IMPL=big selects the first, CTA-per-system SIMT version
+    const char* e = getenv("GSM_LOCAL_IMPL");
+    if (!(e && std::string(e) == "big")) {
+      int rc = gsm_launch_local_krige_mid(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
+                                          d_status);
+      if (rc != GSM_ERR_UNSUPPORTED) return rc;
+    }
     return gsm_launch_local_krige_big(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                       d_status);
+  }
   // Default: the shared-factor kernel for grid targets with more than one block column (k > 8: neighbouring
   // targets share most neighbours, krige_local_shr.cuh), the pipelined kernel otherwise (k <= 8, or explicit
   // points whose order says nothing about their proximity).  GSM_LOCAL_IMPL = shr | pipe | dmma | v1 overrides

@@ -77,31 +77,33 @@ local_krige_big_kernel(BinsDev b, VarioDev v, ModelDev m, int ncon, int centered
   const double ox = s_scale[0], oy = s_scale[1], oz = s_scale[2], isc = s_scale[3];
 
   // ---- assemble: covariance block (lower), then the right-hand-side rows -------------------------
-  for (int e = tid; e < n * n; e += BK_THREADS) {
-    const int r = e % n, c = e / n;
-    if (r < c) continue;
-    double val = v.sill;
-    if (r != c) {
-      const double dx = px[r] - px[c], dy = py[r] - py[c], dz = pz[r] - pz[c];
-      val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+  // thread layout for every 2-D sweep below: 16 row lanes x 8 column lanes (no integer divisions in the loops)
+  const int rx = tid & 15, cy = tid >> 4;
+  for (int c = cy; c < n; c += 8)
+    for (int r = c + rx; r < n; r += 16) {
+      double val = v.sill;
+      if (r != c) {
+        const double dx = px[r] - px[c], dy = py[r] - py[c], dz = pz[r] - pz[c];
+        val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+      }
+      A[c * BK_LD + r] = val;
     }
-    A[c * BK_LD + r] = val;
-  }
-  for (int e = tid; e < nr * n; e += BK_THREADS) {
-    const int q = e / n, c = e % n;
-    double val;
-    if (q == 0) {
-      const double dx = px[c] - tx, dy = py[c] - ty, dz = pz[c] - tz;
-      val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
-    } else if (q == 1) {
-      val = (m.kind == GSM_KRIG_SIMPLE) ? pv[c] - m.mean : pv[c];
-    } else {
-      val = gsm_drift(m, q - 2, (px[c] - ox) * isc, (py[c] - oy) * isc, (pz[c] - oz) * isc);
+  for (int q = cy; q < nr; q += 8)
+    for (int c = rx; c < n; c += 16) {
+      double val;
+      if (q == 0) {
+        const double dx = px[c] - tx, dy = py[c] - ty, dz = pz[c] - tz;
+        val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+      } else if (q == 1) {
+        val = (m.kind == GSM_KRIG_SIMPLE) ? pv[c] - m.mean : pv[c];
+      } else {
+        val = gsm_drift(m, q - 2, (px[c] - ox) * isc, (py[c] - oy) * isc, (pz[c] - oz) * isc);
+      }
+      A[c * BK_LD + n + q] = val;
     }
-    A[c * BK_LD + n + q] = val;
-  }
   // trailing block starts at zero
-  for (int e = tid; e < nr * nr; e += BK_THREADS) A[(n + e / nr) * BK_LD + n + e % nr] = 0.0;
+  for (int q = cy; q < nr; q += 8)
+    for (int c = rx; c < nr; c += 16) A[(n + q) * BK_LD + n + c] = 0.0;
   __syncthreads();
 
   // ---- right-looking Cholesky over the n covariance columns, RHS rows included ------------------
@@ -112,15 +114,11 @@ local_krige_big_kernel(BinsDev b, VarioDev v, ModelDev m, int ncon, int centered
       if (tid == 0) s_bad = 1;
     }
     const double rs = rsqrt(d > 0.0 ? d : 1.0);
-    __syncthreads();
-    for (int r = j + 1 + tid; r < rows; r += BK_THREADS) A[j * BK_LD + r] *= rs;
-    __syncthreads();
-    // A[r][c] -= l_r l_c for j < c <= r, c over covariance columns and the trailing RHS block
-    const int ncols = rows - j - 1;
-    for (int e = tid; e < ncols * ncols; e += BK_THREADS) {
-      const int c = j + 1 + e / ncols, r = j + 1 + e % ncols;
-      if (r < c) continue;
-      A[c * BK_LD + r] = fma(-A[j * BK_LD + r], A[j * BK_LD + c], A[c * BK_LD + r]);
+    // A[r][c] -= l_r l_c for j < c <= r with l = A[.][j] * rs.  Column j is never read again (only the trailing
+    // block is needed), so it is not scaled in place: one barrier per column.
+    for (int c = j + 1 + cy; c < rows; c += 8) {
+      const double lc = A[j * BK_LD + c] * rs;
+      for (int r = c + rx; r < rows; r += 16) A[c * BK_LD + r] = fma(-(A[j * BK_LD + r] * rs), lc, A[c * BK_LD + r]);
     }
     __syncthreads();
   }

@@ -1,0 +1,331 @@
+// Local Kriging for 32 < k <= 64 neighbours (config C5 sweeps k up to 64): one WARP per system, the augmented
+// matrix [C ; B'] in shared memory as 8x8 blocks in the mma.m8n8k4 fragment layout, blocked left-looking
+// Cholesky on the FP64 DMMA path.  Same mathematics as the register-resident kernels (block elimination of the
+// reference's saddle system, krig.jl:58-75 / 316-339 / 245-293): the right-hand sides (c0, z, drift monomials) are
+// carried as extra block rows, so after the last block column the trailing block(s) are -B'C^-1B.
+// Differences from krige_local_shr.cuh / krige_local_pipe.cuh, which keep a 32 x 32 system in registers:
+//   * 36 + 8 blocks do not fit a warp's registers, so blocks live in shared memory (22.5 KB per system) and only
+//     the accumulator of the block being formed is in registers; the block loops are rolled (compact code);
+//   * warps are independent (no diagonal warp, no CTA barriers): the 8 x 8 diagonal blocks are inverted inside the
+//     warp (Gaussian elimination on [A | I] with shuffles);
+//   * covariances are evaluated directly (no pooling across neighbouring targets).
+// It replaces the CTA-per-system SIMT kernel (krige_local_big.cu, kept as GSM_LOCAL_IMPL=big) as the k > 32 path.
+#include <algorithm>
+
+#include "gsm_internal.cuh"
+#include "krige_cov_fast.cuh"
+
+namespace {
+
+constexpr int MW = 4;                // system warps per CTA
+constexpr int MKMAX = GSM_MAX_NEIGHBORS;   // 64
+constexpr int MNBC = MKMAX / 8;      // 8 block columns at most
+
+__device__ __forceinline__ void dmma_m(double2& d, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(d.x), "+d"(d.y)
+      : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double rsqrt_m(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-(d * y), y, 1.0);
+  const double p = e * fma(e, 0.375, 0.5);
+  return fma(y, p, y);
+}
+
+// Warp-cooperative inverse Cholesky factor of an 8x8 SPD block in fragment layout (lane (g,t) owns A[g][2t],
+// A[g][2t+1]): Gaussian elimination without pivoting on [A | I] gives the unit-lower inverse M; scaling row g by
+// 1/sqrt(pivot g) turns it into W = L^-1 with A = L L'.
+__device__ __forceinline__ double2 inv_chol_warp(double2 a, int g, int t, bool& bad) {
+  double2 m = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);
+  double myrs = 1.0;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const double ac = (j & 1) ? a.y : a.x;
+    double d = gsm_shfl(ac, j * 4 + (j >> 1));            // pivot A[j][j]
+    const double arj = gsm_shfl(ac, g * 4 + (j >> 1));    // A[g][j]
+    const double pj0 = gsm_shfl(a.x, j * 4 + t), pj1 = gsm_shfl(a.y, j * 4 + t);   // pivot row of A
+    const double mj0 = gsm_shfl(m.x, j * 4 + t), mj1 = gsm_shfl(m.y, j * 4 + t);   // pivot row of M
+    if (!(d > 0.0)) {
+      bad = true;
+      d = 1.0;
+    }
+    const double rs = rsqrt_m(d);
+    if (g == j) myrs = rs;
+    const double f = (g > j) ? -((arj * rs) * rs) : 0.0;
+    a.x = fma(f, pj0, a.x);
+    a.y = fma(f, pj1, a.y);
+    m.x = fma(f, mj0, m.x);
+    m.y = fma(f, mj1, m.y);
+  }
+  return make_double2(m.x * myrs, m.y * myrs);
+}
+
+// blocks of one system: lower triangle of the covariance part, then NRB right-hand-side block rows
+__host__ __device__ constexpr int mid_blocks(int nrb) { return MNBC * (MNBC + 1) / 2 + nrb * MNBC; }
+
+template <int NRB>
+struct MidWarp {
+  double blk[mid_blocks(NRB)][64];
+  double px[MKMAX], py[MKMAX], pz[MKMAX], pv[MKMAX];
+  double G[NRB * (NRB + 1) / 2][64];
+  int sp[MKMAX];
+};
+
+template <int NRB>
+__global__ void __launch_bounds__(MW * 32)
+local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant__ VarioDev v,
+                       const __grid_constant__ ModelDev m, const __grid_constant__ gsm_cov::CovFast cf, int ncon,
+                       int centered, const __grid_constant__ TargetsDev tg, int k, int minn,
+                       const int* __restrict__ pos,
+                       const int* __restrict__ cnt, double* __restrict__ out_mean, double* __restrict__ out_var,
+                       unsigned char* __restrict__ out_status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  MidWarp<NRB>& S = reinterpret_cast<MidWarp<NRB>*>(smem_raw)[warp];
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const int nr = 2 + ncon;
+  constexpr int NGB = NRB * (NRB + 1) / 2;
+
+  auto lowidx = [](int I, int J) { return I * (I + 1) / 2 + J; };   // J <= I < nbc
+  auto frag = [&](const double* src) -> double2 { return *reinterpret_cast<const double2*>(&src[g * 8 + 2 * t]); };
+  auto put = [&](double* dst, const double2& val) { *reinterpret_cast<double2*>(&dst[g * 8 + 2 * t]) = val; };
+  auto upd = [&](double2& A, const double2& X, const double2& Y) {   // A -= X Y'
+    dmma_m(A, -X.x, Y.x);
+    dmma_m(A, -X.y, Y.y);
+  };
+  auto panel = [&](double2& X, const double2& W) {                   // X <- X W'
+    double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+    dmma_m(a0, X.x, W.x);
+    dmma_m(a1, X.y, W.y);
+    X = make_double2(a0.x + a1.x, a0.y + a1.y);
+  };
+
+  const long long nwarps = (long long)gridDim.x * MW;
+  for (long long tt = blockIdx.x * (long long)MW + warp; tt < tg.count; tt += nwarps) {
+    int n = cnt[tt];
+    if (n < minn || n <= 0) {
+      if (lane == 0) {
+        out_mean[tt] = qnan;
+        if (out_var) out_var[tt] = qnan;
+        if (out_status) out_status[tt] = GSM_ST_MISSING;
+      }
+      continue;
+    }
+    n = min(n, min(k, MKMAX));
+    const int nbc = (n + 7) >> 3;                       // block columns of this system
+    double tx, ty, tz;
+    gsm_target_coords(tg, tg.first + tt, tx, ty, tz);
+
+    // ---- canonical neighbour order: ascending record position (rank by counting, two entries per lane) ----
+    __syncwarp();
+    const int p0 = lane < n ? pos[tt * (long long)k + lane] : 0x7fffffff;
+    const int p1 = lane + 32 < n ? pos[tt * (long long)k + lane + 32] : 0x7fffffff;
+    S.sp[lane] = p0;
+    S.sp[lane + 32] = p1;
+    __syncwarp();
+    int r0 = 0, r1 = 0;
+    for (int j = 0; j < n; ++j) {
+      const int pj = S.sp[j];
+      r0 += pj < p0 ? 1 : 0;
+      r1 += pj < p1 ? 1 : 0;
+    }
+    if (lane < n) {
+      const double4 r = b.rec[p0];
+      S.px[r0] = r.x, S.py[r0] = r.y, S.pz[r0] = r.z, S.pv[r0] = r.w;
+    }
+    if (lane + 32 < n) {
+      const double4 r = b.rec[p1];
+      S.px[r1] = r.x, S.py[r1] = r.y, S.pz[r1] = r.z, S.pv[r1] = r.w;
+    }
+    __syncwarp();
+    // drift scaling: centre at the target, scale by the neighbourhood radius (lower-set exponent tables)
+    double ox = 0.0, oy = 0.0, oz = 0.0, isc = 1.0;
+    if (centered) {
+      double dmax = 0.0;
+      for (int i = lane; i < n; i += 32) {
+        const double dx = S.px[i] - tx, dy = S.py[i] - ty, dz = S.pz[i] - tz;
+        dmax = fmax(dmax, dx * dx + dy * dy + dz * dz);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, gsm_shfl_xor(dmax, o));
+      ox = tx, oy = ty, oz = tz;
+      isc = dmax > 0.0 ? rsqrt(dmax) : 1.0;
+    }
+
+    // ---- assemble the blocks (fragment layout); empty slots are identity rows / columns ----
+    for (int I = 0; I < nbc; ++I)
+      for (int J = 0; J <= I; ++J) {
+        const int row = 8 * I + g, c0 = 8 * J + 2 * t;
+        double e[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int col = c0 + s;
+          double val = (row == col) ? 1.0 : 0.0;
+          if (row < n && col < n) {
+            val = v.sill;
+            if (row != col) {
+              const double dx = S.px[row] - S.px[col], dy = S.py[row] - S.py[col], dz = S.pz[row] - S.pz[col];
+              val = gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+            }
+          }
+          e[s] = val;
+        }
+        put(S.blk[lowidx(I, J)], make_double2(e[0], e[1]));
+      }
+    const int rbase = MNBC * (MNBC + 1) / 2;            // right-hand-side blocks: rbase + R * MNBC + J
+    for (int R = 0; R < NRB; ++R)
+      for (int J = 0; J < nbc; ++J) {
+        const int q = 8 * R + g, c0 = 8 * J + 2 * t;
+        double e[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int c = c0 + s;
+          double val = 0.0;
+          if (q < nr && c < n) {
+            if (q == 0) {
+              const double dx = S.px[c] - tx, dy = S.py[c] - ty, dz = S.pz[c] - tz;
+              val = gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+            } else if (q == 1) {
+              val = (m.kind == GSM_KRIG_SIMPLE) ? S.pv[c] - m.mean : S.pv[c];
+            } else {
+              val = gsm_drift(m, q - 2, (S.px[c] - ox) * isc, (S.py[c] - oy) * isc, (S.pz[c] - oz) * isc);
+            }
+          }
+          e[s] = val;
+        }
+        put(S.blk[rbase + R * MNBC + J], make_double2(e[0], e[1]));
+      }
+    __syncwarp();
+
+    // ---- left-looking blocked Cholesky, right-hand-side rows included; blocks are overwritten by L ----
+    bool bad = false;
+    double2 Gacc[NGB];
+#pragma unroll
+    for (int q = 0; q < NGB; ++q) Gacc[q] = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int kb = 0; kb < nbc; ++kb) {
+      // diagonal block
+      double2 D = frag(S.blk[lowidx(kb, kb)]);
+#pragma unroll 1
+      for (int j = 0; j < kb; ++j) {
+        const double2 L = frag(S.blk[lowidx(kb, j)]);
+        upd(D, L, L);
+      }
+      const double2 W = inv_chol_warp(D, g, t, bad);
+      // blocks below it, then the right-hand-side rows
+#pragma unroll 1
+      for (int i = kb + 1; i < nbc + NRB; ++i) {
+        const bool rhs = i >= nbc;
+        double* bi = rhs ? S.blk[rbase + (i - nbc) * MNBC + kb] : S.blk[lowidx(i, kb)];
+        double2 C = frag(bi);
+#pragma unroll 1
+        for (int j = 0; j < kb; ++j) {
+          const double2 X = frag(rhs ? S.blk[rbase + (i - nbc) * MNBC + j] : S.blk[lowidx(i, j)]);
+          const double2 Y = frag(S.blk[lowidx(kb, j)]);
+          upd(C, X, Y);
+        }
+        panel(C, W);
+        put(bi, C);
+      }
+      __syncwarp();
+      // Schur blocks: G[r][q] -= L_Rr,kb L_Rq,kb'
+#pragma unroll
+      for (int r = 0; r < NRB; ++r)
+#pragma unroll
+        for (int q = 0; q <= r; ++q) {
+          const double2 X = frag(S.blk[rbase + r * MNBC + kb]), Y = frag(S.blk[rbase + q * MNBC + kb]);
+          upd(Gacc[r * (r + 1) / 2 + q], X, Y);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NGB; ++q) put(S.G[q], Gacc[q]);
+    const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+    __syncwarp();
+
+    // ---- epilogue (one lane): -G[a][b], a >= b, stored as 8x8 blocks (0,0), (1,0), (1,1) ----
+    if (lane == 0) {
+      bool singular = anybad != 0;
+      auto Gm = [&](int a, int bb) -> double {
+        const int br = a >> 3, bc = bb >> 3;
+        return -S.G[br * (br + 1) / 2 + bc][(a & 7) * 8 + (bb & 7)];
+      };
+      const double uu = Gm(0, 0), wu = Gm(1, 0);
+      const double c0 = v.sill;
+      double mean, var;
+      if (ncon == 0) {
+        mean = m.mean + wu;
+        var = c0 - uu;
+      } else {
+        double Gs[GSM_MAX_DRIFT * GSM_MAX_DRIFT], gq[GSM_MAX_DRIFT], hw[GSM_MAX_DRIFT], y[GSM_MAX_DRIFT], hy[GSM_MAX_DRIFT];
+        for (int p = 0; p < ncon; ++p) {
+          const double f0 = (m.kind == GSM_KRIG_ORDINARY) ? 1.0
+                                                           : gsm_drift(m, p, (tx - ox) * isc, (ty - oy) * isc, (tz - oz) * isc);
+          gq[p] = Gm(2 + p, 0) - f0;
+          hw[p] = Gm(2 + p, 1);
+          for (int q = 0; q <= p; ++q) Gs[p * ncon + q] = Gm(2 + p, 2 + q);
+        }
+        for (int j = 0; j < ncon; ++j) {
+          double d = Gs[j * ncon + j];
+          if (!(d > 0.0)) {
+            singular = true;
+            d = 1.0;
+          }
+          const double rs = rsqrt(d);
+          Gs[j * ncon + j] = rs;
+          for (int i = j + 1; i < ncon; ++i) Gs[i * ncon + j] *= rs;
+          for (int i = j + 1; i < ncon; ++i)
+            for (int q = j + 1; q <= i; ++q) Gs[i * ncon + q] = fma(-Gs[i * ncon + j], Gs[q * ncon + j], Gs[i * ncon + q]);
+        }
+        double gnu = 0.0, hnu = 0.0;
+        for (int i = 0; i < ncon; ++i) {
+          double s1 = gq[i], s2 = hw[i];
+          for (int q = 0; q < i; ++q) {
+            s1 = fma(-Gs[i * ncon + q], y[q], s1);
+            s2 = fma(-Gs[i * ncon + q], hy[q], s2);
+          }
+          y[i] = s1 * Gs[i * ncon + i];
+          hy[i] = s2 * Gs[i * ncon + i];
+          gnu = fma(y[i], y[i], gnu);
+          hnu = fma(hy[i], y[i], hnu);
+        }
+        mean = wu - hnu;
+        var = c0 - uu + gnu;
+      }
+      var += 1e-10;  // krig.jl:278-279
+      out_mean[tt] = singular ? qnan : mean;
+      if (out_var) out_var[tt] = singular ? qnan : var;
+      if (out_status) out_status[tt] = singular ? GSM_ST_SINGULAR : GSM_ST_OK;
+    }
+  }
+}
+
+template <int NRB>
+int launch_mid(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered, const TargetsDev& tg, int k,
+               int minn, const int* pos, const int* cnt, double* mean, double* var, unsigned char* status) {
+  const size_t smem = sizeof(MidWarp<NRB>) * MW;
+  auto kern = local_krige_mid_kernel<NRB>;
+  GSM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = (int)std::max<size_t>(1, (227 * 1024) / (smem + 1024));
+  const long long want = (tg.count + MW - 1) / MW;
+  const int blocks = (int)std::min<long long>(want, 148LL * per_sm);
+  kern<<<blocks, MW * 32, smem, ctx->stream>>>(ctx->bins, v, m, gsm_cov::make_cov(v), ncon, centered, tg, k, minn, pos, cnt,
+                                               mean, var, status);
+  ctx->tim.launches++;
+  GSM_CUDA(ctx, cudaGetLastError());
+  return GSM_OK;
+}
+
+}  // namespace
+
+int gsm_launch_local_krige_mid(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
+                               const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                               double* d_mean, double* d_var, unsigned char* d_status) {
+  if (k > MKMAX || k < 1 || ncon > GSM_MAX_DRIFT) return GSM_ERR_UNSUPPORTED;
+  if (tg.count <= 0) return GSM_OK;
+  if (2 + ncon > 8)
+    return launch_mid<2>(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var, d_status);
+  return launch_mid<1>(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var, d_status);
+}

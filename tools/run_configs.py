@@ -131,7 +131,7 @@ def c5():
             rng = np.random.default_rng(5)
             X = rng.uniform(0, dims[0], size=(n, dim)); z = rng.standard_normal(n)
             tab = gsm.georef({"z": z}, gsm.PointSet(X)); grid = gsm.CartesianGrid(*dims)
-            for k in (8, 16, 32):
+            for k in (8, 16, 32, 64):
                 sk = gsm.SimpleKriging(gsm.SphericalVariogram(range=dims[0] / 20, nugget=0.1), float(z.mean()))
                 _, dt = timed(lambda: gsm.fitpredict(sk, tab, grid, maxneighbors=k, prob=True, ctx=ctx), reps=1)
                 t = ctx.timings()
