@@ -22,7 +22,7 @@ GSM_TARGETS_GRID, GSM_TARGETS_POINTS = 0, 1
 
 EXPORTED_SYMBOLS = [
     "gsm_abi_version", "gsm_create", "gsm_destroy", "gsm_last_error", "gsm_get_timings", "gsm_get_summary", "gsm_synchronize",
-    "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_knn", "gsm_local_krige",
+    "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_set_samples_scaled", "gsm_knn", "gsm_local_krige",
     "gsm_global_krige_fit", "gsm_global_krige_status", "gsm_global_krige_predict", "gsm_global_krige_free",
     "gsm_idw", "gsm_measure_fp64_peak",
 ]
@@ -97,6 +97,7 @@ def load():
     lib.gsm_host_alloc.argtypes = [P(vp), i64]
     lib.gsm_host_free.argtypes = [vp]
     lib.gsm_set_samples.argtypes = [vp, vp, i32, i64, vp]
+    lib.gsm_set_samples_scaled.argtypes = [vp, vp, i32, i64, vp, C.c_double, P(C.c_double), P(C.c_int64)]
     lib.gsm_knn.argtypes = [vp, P(Targets), P(NeighborOpts), vp, vp]
     lib.gsm_local_krige.argtypes = [vp, P(Variogram), P(Model), P(Targets), P(NeighborOpts), vp, vp, vp, vp]
     lib.gsm_global_krige_fit.argtypes = [vp, P(Variogram), P(Model), P(vp)]
@@ -211,6 +212,23 @@ class Context:
         self._keep = (coords, values)
         self._check(self._lib.gsm_set_samples(self._h, _ptr(coords), int(dim), int(n), _ptr(values)))
         self.dim, self.n = int(dim), int(n)
+
+    def set_samples_scaled(self, coords, values, scale_floor):
+        """Upload RAW coordinates; absmax, alpha = 1 / max(scale_floor, absmax) and the scaling happen on the device
+        (gsm_set_samples_scaled).  Returns (alpha, number of NaN values)."""
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        if coords.ndim == 1:
+            coords = coords[:, None]
+        n, dim = coords.shape
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if values.shape != (n,):
+            raise ValueError("values must have one entry per sample")
+        self._keep = (coords, values)
+        alpha, nan = C.c_double(0.0), C.c_int64(0)
+        self._check(self._lib.gsm_set_samples_scaled(self._h, _ptr(coords), int(dim), int(n), _ptr(values),
+                                                     C.c_double(float(scale_floor)), C.byref(alpha), C.byref(nan)))
+        self.dim, self.n = int(dim), int(n)
+        return float(alpha.value), int(nan.value)
 
     # ---- descriptors -----------------------------------------------------------------------
     @staticmethod

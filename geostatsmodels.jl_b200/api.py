@@ -409,15 +409,15 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     if len(names) != 1:
         raise NotImplementedError("GPU path claims univariate tables only")
     z = np.asarray(data.table[names[0]], dtype=np.float64)
-    if np.isnan(z).any():
-        raise NotImplementedError("missing values are not claimed by the GPU path")
     X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
-    alpha = _scale_factor(model, data.domain, dom)     # _scale, models.jl:118
     ctx = ctx or default_context(device)
-    sx, sz = _stage(ctx, X.shape[0], X.shape[1])
-    np.multiply(X, alpha, out=sx)                      # dat |> Scale(alpha), models.jl:279, into pinned memory
-    np.copyto(sz, z)
-    ctx.set_samples(sx, sz)
+    # _scale (models.jl:272-291) on the device: the raw coordinates are uploaded as they are (straight DMA when the
+    # caller's arrays are page-locked), absmax / alpha / `dat |> Scale(alpha)` / the NaN check run as kernels
+    r = model._range()
+    floor = max(1.0 if math.isinf(r) else r, dom._absmax())
+    alpha, nnan = ctx.set_samples_scaled(X, z, floor)
+    if nnan:
+        raise NotImplementedError("missing values are not claimed by the GPU path")
     out = out or {}
     t = _targets_for(dom, alpha, first, count)
     radius = 0.0
@@ -466,15 +466,6 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     pred.domain = out_dom if out_dom is not None else dom   # georef over the ORIGINAL domain, models.jl:128
     pred.shard = (first, M)
     return pred
-
-
-def _stage(ctx, n, dim):
-    """Page-locked staging for the scaled sample coordinates / values so the upload is one async DMA."""
-    st = getattr(ctx, "_stage_bufs", None)
-    if st is None or st[0].shape != (n, dim):
-        st = (_lib.PinnedArray((n, dim), np.float64), _lib.PinnedArray((n,), np.float64))
-        ctx._stage_bufs = st
-    return st[0].array, st[1].array
 
 
 def _clamp_max(maxneighbors, nobs):

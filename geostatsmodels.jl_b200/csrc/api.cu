@@ -225,6 +225,29 @@ __global__ void summary_kernel(const unsigned char* __restrict__ st, const doubl
   }
 }
 
+// max |coords| (bit pattern of a non-negative double orders like an integer) and NaN count of the values
+__global__ void absmax_nan_kernel(const double* __restrict__ c, long long nc, const double* __restrict__ v, long long nv,
+                                  unsigned long long* __restrict__ out) {
+  double mx = 0.0;
+  int nan = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nc; i += (long long)gridDim.x * blockDim.x) {
+    mx = fmax(mx, fabs(c[i]));
+    if (i < nv && v[i] != v[i]) nan++;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    nan += __shfl_xor_sync(0xffffffffu, nan, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(mx));
+    if (nan) atomicAdd(&out[1], (unsigned long long)nan);
+  }
+}
+__global__ void scale_kernel(double* __restrict__ c, long long nc, double alpha) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < nc) c[i] = __dmul_rn(c[i], alpha);
+}
+
 struct EventTimer {
   std::vector<cudaEvent_t> evs;
   cudaEvent_t mark(cudaStream_t st) {
@@ -333,7 +356,8 @@ int gsm_host_free(void* p) {
   return cudaFreeHost(p) == cudaSuccess ? GSM_OK : GSM_ERR_CUDA;
 }
 
-int gsm_set_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values) {
+static int set_samples_impl(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values,
+                            bool scaled, double scale_floor, double* out_alpha, int64_t* out_nan) {
   if (!ctx) return GSM_ERR_INVALID;
   if (!coords || !values || dim < 1 || dim > 3 || n < 1) {
     gsm_set_error(ctx, "gsm_set_samples: need coords, values, 1 <= dim <= 3 and n >= 1");
@@ -347,6 +371,25 @@ int gsm_set_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, 
   GSM_CHECK(gsm_reserve(ctx, ctx->values, (size_t)n * sizeof(double)));
   GSM_CUDA(ctx, cudaMemcpyAsync(ctx->coords.p, coords, (size_t)n * dim * sizeof(double), cudaMemcpyDefault, ctx->stream));
   GSM_CUDA(ctx, cudaMemcpyAsync(ctx->values.p, values, (size_t)n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  if (scaled) {
+    GSM_CHECK(gsm_reserve(ctx, ctx->summ_dev, 4 * sizeof(unsigned long long)));
+    unsigned long long* d = (unsigned long long*)ctx->summ_dev.p;
+    GSM_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    const long long nc = (long long)n * dim;
+    const int blocks = (int)std::min<long long>((nc + 255) / 256, 148 * 8);
+    absmax_nan_kernel<<<blocks, 256, 0, ctx->stream>>>((const double*)ctx->coords.p, nc, (const double*)ctx->values.p, n, d);
+    unsigned long long h[2] = {0, 0};
+    GSM_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double absmax;
+    static_assert(sizeof(double) == sizeof(unsigned long long), "bit cast");
+    memcpy(&absmax, &h[0], sizeof(double));
+    const double alpha = 1.0 / std::max(scale_floor, absmax);
+    if (out_alpha) *out_alpha = alpha;
+    if (out_nan) *out_nan = (int64_t)h[1];
+    scale_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>((double*)ctx->coords.p, nc, alpha);
+    ctx->tim.launches += 2;
+  }
   cudaEvent_t e1 = et.mark(ctx->stream);
   ctx->dim = dim;
   ctx->n = n;
@@ -361,6 +404,19 @@ int gsm_set_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, 
   ctx->tim.bin_ms = EventTimer::ms(e1, e2);
   ctx->tim.total_ms = EventTimer::ms(e0, e2);
   return GSM_OK;
+}
+
+int gsm_set_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values) {
+  return set_samples_impl(ctx, coords, dim, n, values, false, 1.0, nullptr, nullptr);
+}
+
+int gsm_set_samples_scaled(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values,
+                           double scale_floor, double* out_alpha, int64_t* out_nan) {
+  if (!(scale_floor > 0.0)) {
+    gsm_set_error(ctx, "gsm_set_samples_scaled: scale_floor must be positive");
+    return GSM_ERR_INVALID;
+  }
+  return set_samples_impl(ctx, coords, dim, n, values, true, scale_floor, out_alpha, out_nan);
 }
 
 // Shared driver of the neighbourhood-based entry points.

@@ -149,6 +149,15 @@ GSM_API int gsm_host_free(void* p);
  * Builds the grid bins used by the neighbour search (KNearestSearch construction, models.jl:155). */
 GSM_API int gsm_set_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values);
 
+/* Same, with the reference's `_scale` (models.jl:272-291) done on the device: uploads the RAW coordinates,
+ * reduces absmax = max |coordinate|, sets alpha = 1 / max(scale_floor, absmax) -- the caller passes
+ * scale_floor = max(variogram range (1 if infinite), absmax of the target domain) -- multiplies the coordinates
+ * by alpha (one rounding each, like `dat |> Scale(alpha)`) and builds the bins.  out_alpha receives alpha (the
+ * caller scales targets, radius and variogram with it); out_nan the number of NaN values (missing data are not
+ * claimed by the GPU path).  The host never walks the sample arrays. */
+GSM_API int gsm_set_samples_scaled(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values,
+                           double scale_floor, double* out_alpha, int64_t* out_nan);
+
 /* ---- test hook: Meshes `search!` (models.jl:164).  out_idx: M x k int32 (0-based sample rows,
  * ascending by (d2, index); unused slots = -1), out_n: M int32 neighbours found. host or device. */
 GSM_API int gsm_knn(gsm_ctx* ctx, const gsm_targets* targets, const gsm_neighbor_opts* opts,
