@@ -127,6 +127,50 @@ def _ptr(a):
     raise TypeError(f"cannot take the address of {type(a)}")
 
 
+class _PinnedPool:
+    """Result arrays in page-locked memory without asking the caller for them: buffers are recycled when the last
+    numpy view of a result dies (finalizer on the ctypes buffer every view keeps alive), so steady-state calls DMA
+    straight into pinned memory and pay no cudaHostAlloc."""
+
+    CAP = 2 << 30   # pooled (idle) bytes kept at most
+
+    def __init__(self):
+        self._free, self._idle = {}, 0
+
+    def empty(self, shape, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        shape = tuple(int(x) for x in np.atleast_1d(shape))
+        count = int(np.prod(shape))
+        key = max(4096, -(-count * dtype.itemsize // 4096) * 4096)
+        lst = self._free.get(key)
+        if lst:
+            ptr = lst.pop()
+            self._idle -= key
+        else:
+            p = C.c_void_p()
+            rc = load().gsm_host_alloc(C.byref(p), key)
+            if rc != GSM_OK:
+                return np.empty(shape, dtype)   # pinning failed (limits): pageable memory still works
+            ptr = p.value
+        buf = (C.c_char * key).from_address(ptr)
+        weakref.finalize(buf, self._release, key, ptr)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _release(self, key, ptr):
+        try:
+            if self._idle + key <= self.CAP:
+                self._free.setdefault(key, []).append(ptr)
+                self._idle += key
+            else:
+                load().gsm_host_free(C.c_void_p(ptr))
+        except Exception:
+            pass
+
+
+_pool = _PinnedPool()
+
+
 class PinnedArray:
     """A numpy view over page-locked host memory from gsm_host_alloc (outputs DMA straight into it)."""
 
@@ -280,9 +324,9 @@ class Context:
                     radius: float = 0.0, want_var=True, want_neighbors=False, out_mean=None, out_var=None,
                     out_status=None):
         M = self.target_count(targets)
-        mean = np.empty(M) if out_mean is None else out_mean
-        var = (np.empty(M) if out_var is None else out_var) if want_var else None
-        status = np.empty(M, dtype=np.uint8) if out_status is None else out_status
+        mean = _pool.empty(M, np.float64) if out_mean is None else out_mean
+        var = (_pool.empty(M, np.float64) if out_var is None else out_var) if want_var else None
+        status = _pool.empty(M, np.uint8) if out_status is None else out_status
         nbr = None
         if want_neighbors:
             k = min(maxneighbors, self.n) if 1 <= maxneighbors <= self.n else self.n
@@ -295,8 +339,8 @@ class Context:
     def idw(self, exponent: float, targets: Targets, maxneighbors: int = 0, minneighbors: int = 1,
             radius: float = 0.0, out_mean=None):
         M = self.target_count(targets)
-        mean = np.empty(M) if out_mean is None else out_mean
-        status = np.empty(M, dtype=np.uint8)
+        mean = _pool.empty(M, np.float64) if out_mean is None else out_mean
+        status = _pool.empty(M, np.uint8)
         o = NeighborOpts(int(maxneighbors), int(minneighbors), float(radius)) if maxneighbors != 0 else None
         self._check(self._lib.gsm_idw(self._h, float(exponent), C.byref(targets),
                                       C.byref(o) if o is not None else None, _ptr(mean), _ptr(status)))
@@ -322,8 +366,8 @@ class GlobalFit:
 
     def predict(self, targets: Targets, want_var=True, out_mean=None, out_var=None):
         M = Context.target_count(targets)
-        mean = np.empty(M) if out_mean is None else out_mean
-        var = (np.empty(M) if out_var is None else out_var) if want_var else None
+        mean = _pool.empty(M, np.float64) if out_mean is None else out_mean
+        var = (_pool.empty(M, np.float64) if out_var is None else out_var) if want_var else None
         self.ctx._check(self.ctx._lib.gsm_global_krige_predict(self._h, C.byref(targets), _ptr(mean), _ptr(var)))
         return mean, var
 
