@@ -40,11 +40,11 @@ for _ in range(2):
 print(ctx.timings())
 T = tr.cpu().numpy().reshape(4, 10, 16)
 base = T[0, 0, 0]
-ns = ["start", "prepped", "poolbar", "slot", "X1+bar", "X2", "Q1Q4", "fin", "endbar"]
+ns = ["start", "prepped", "-", "slot", "landed", "Q1", "Q4", "fin", "endbar"]
 nd = ["woke", "done", "epi-done"]
 nf = ["start", "hashed", "ranked", "FFREE", "published", "factored"]
 for it in range(4):
     print(f"--- job {20 + it}")
     for w in (0, 5):
-        print(f"  sys{w}: " + ", ".join(f"{ns[s]}={T[it, w, s] - base}" for s in range(9)))
+        print(f"  sys{w}: " + ", ".join(f"{ns[s]}={T[it, w, s] - base}" for s in range(9) if s != 2))
     print("  diag: " + ", ".join(f"{nd[s]}={T[it, 8, s] - base}" for s in range(3)))
