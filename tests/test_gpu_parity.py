@@ -543,3 +543,77 @@ def test_shared_factor_kernel_tiny_and_degenerate_grids(gsm, oracle, dims, k):
     got = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=k, prob=True).z
     assert (st == 0).all()
     assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL) and np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL)
+
+
+def test_full_size_c3_properties_and_parity(gsm, oracle):
+    """BASELINE config C3 at full size (200 k samples -> 2048 x 2048 grid, local OK, k = 32): size-independent
+    properties over all 4.19 M targets (the OK weights sum to one, so an affine map of the data maps the means
+    affinely and leaves the variances alone), and parity against the C oracle on a strided subsample."""
+    import gsm_oracle_c as oc
+    o = oracle
+    rng = np.random.default_rng(3)
+    n = 200_000
+    X = rng.uniform(0, 2048, size=(n, 2))
+    z = np.sin(X[:, 0] / 20) + np.cos(X[:, 1] / 30) + 0.1 * rng.standard_normal(n)
+    gm = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=50.0, sill=1.0, nugget=0.1))
+    grid = gsm.CartesianGrid(2048, 2048)
+    p1 = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=32, prob=True).z
+    mu1, var1 = np.array(p1.mu), np.array(p1.sigma)
+    p2 = gsm.fitpredict(gm, gsm.georef({"z": 2.0 * z + 1.0}, gsm.PointSet(X)), grid, maxneighbors=32, prob=True).z
+    assert np.isfinite(mu1).all() and (var1 > 0).all()
+    assert np.array_equal(var1, p2.sigma)                                     # the variance never sees the data
+    assert np.allclose(p2.mu, 2.0 * mu1 + 1.0, rtol=1e-12, atol=1e-12)
+    assert var1.max() <= 1.0 + 0.1 + 1e-9                                     # bounded by sill (+ Lagrange term < nugget)
+    om = o.ordinary_kriging(o.Variogram(o.SPHERICAL, 1.0, 0.1, 50.0))
+    idx = np.unique(np.linspace(0, 2048 * 2048 - 1, 3000).astype(np.int64))
+    og = o.Grid((0.0, 0.0), (1.0, 1.0), (2048, 2048))
+    T = og.centroids()[idx]
+
+    class _Dom(np.ndarray):
+        pass
+
+    dom = np.asarray(T).view(_Dom)
+    orig = o._dom_absmax
+    o._dom_absmax = lambda d: og.bbox_absmax() if isinstance(d, _Dom) else orig(d)
+    try:
+        mu, var, st, _, _ = oc.fitpredict(om, X, z, dom, prob=True, maxneighbors=32, nthreads=8)
+    finally:
+        o._dom_absmax = orig
+    assert (st == 0).all()
+    assert np.allclose(mu1[idx], mu, rtol=RTOL, atol=ATOL) and np.allclose(var1[idx], var, rtol=RTOL, atol=ATOL)
+
+
+def test_full_size_north_star_3d(gsm, oracle):
+    """The north-star target of BASELINE.json: local OK, k = 32, 1 M 3-D samples -> 256^3 grid, at full size:
+    affine-data property over all 16.7 M targets and parity against the C oracle on a strided subsample."""
+    import gsm_oracle_c as oc
+    o = oracle
+    rng = np.random.default_rng(6)
+    n = 1_000_000
+    X = rng.uniform(0, 256, size=(n, 3))
+    z = np.sin(X[:, 0] / 20) + np.cos(X[:, 2] / 30) + 0.1 * rng.standard_normal(n)
+    gm = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=20.0, sill=1.0, nugget=0.1))
+    grid = gsm.CartesianGrid(256, 256, 256)
+    p1 = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=32, prob=True).z
+    mu1, var1 = np.array(p1.mu), np.array(p1.sigma)
+    p2 = gsm.fitpredict(gm, gsm.georef({"z": 0.5 * z - 3.0}, gsm.PointSet(X)), grid, maxneighbors=32, prob=True).z
+    assert np.isfinite(mu1).all() and (var1 > 0).all()
+    assert np.array_equal(var1, p2.sigma)
+    assert np.allclose(p2.mu, 0.5 * mu1 - 3.0, rtol=1e-12, atol=1e-12)
+    om = o.ordinary_kriging(o.Variogram(o.SPHERICAL, 1.0, 0.1, 20.0))
+    idx = np.unique(np.linspace(0, 256 ** 3 - 1, 1500).astype(np.int64))
+    og = o.Grid((0.0,) * 3, (1.0,) * 3, (256, 256, 256))
+    T = np.stack([og.centroids(int(i), 1)[0] for i in idx])
+
+    class _Dom(np.ndarray):
+        pass
+
+    dom = np.asarray(T).view(_Dom)
+    orig = o._dom_absmax
+    o._dom_absmax = lambda d: og.bbox_absmax() if isinstance(d, _Dom) else orig(d)
+    try:
+        mu, var, st, _, _ = oc.fitpredict(om, X, z, dom, prob=True, maxneighbors=32, nthreads=8)
+    finally:
+        o._dom_absmax = orig
+    assert (st == 0).all()
+    assert np.allclose(mu1[idx], mu, rtol=RTOL, atol=ATOL) and np.allclose(var1[idx], var, rtol=RTOL, atol=ATOL)
