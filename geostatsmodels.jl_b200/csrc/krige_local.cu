@@ -15,6 +15,8 @@
 //   prediction, is unchanged while G stays well conditioned); otherwise on the raw coordinates.
 #include <cstdlib>
 
+#include <cmath>
+
 #include "gsm_internal.cuh"
 
 namespace {
@@ -275,7 +277,23 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   // points whose order says nothing about their proximity).  GSM_LOCAL_IMPL = shr | pipe | dmma | v1 overrides
   // (A/B profiling; read per call so one process can compare them).
   const char* impl_env = getenv("GSM_LOCAL_IMPL");
-  const bool patches = tg.kind == GSM_TARGETS_GRID && tg.dim >= 2 && tg.dims[1] > 1;
+  bool patches = tg.kind == GSM_TARGETS_GRID && tg.dim >= 2 && tg.dims[1] > 1;
+  if (patches) {
+    // Sharing pays when the neighbourhood is wide compared with a patch: radius of the k nearest samples in units
+    // of the target spacing, from the mean sample density of the bins.  Measured crossover (tools/ab_dense.py,
+    // tools/run_configs.py): ~5 cells in 2-D (4 x 2 patches), ~3 in 3-D (2 x 2 x 2); below it the pools overflow
+    // or share little and the per-system pipelined kernel is faster.
+    const BinsDev& bn = ctx->bins;
+    const int d = tg.dim >= 3 ? 3 : 2;
+    double cells = (double)bn.nc[0] * bn.nc[1] * (d == 3 ? bn.nc[2] : 1);
+    double vol = cells * std::pow(bn.h, d);
+    double cellvol = std::fabs(tg.spacing[0] * tg.spacing[1] * (d == 3 ? tg.spacing[2] : 1.0));
+    if (vol > 0.0 && cellvol > 0.0 && ctx->n > 0) {
+      const double s = (double)ctx->n / vol * cellvol;   // samples per target cell
+      const double rk = d == 3 ? std::cbrt(3.0 * k / (4.0 * M_PI * s)) : std::sqrt(k / (M_PI * s));
+      if (rk < (d == 3 ? 3.0 : 5.0)) patches = false;
+    }
+  }
   const std::string impl = impl_env ? impl_env : ((k > 8 && patches) ? "shr" : "pipe");
   if (impl == "shr") {
     int rc = gsm_launch_local_krige_shr(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
