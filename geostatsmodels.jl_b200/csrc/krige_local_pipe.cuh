@@ -352,9 +352,10 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
   // P2+P3: coordinates / right-hand-side rows into buffer `bf`, hash insert, pool ids for owners
   auto P23 = [&](int bf) {
     const bool live = lane < x_n;
-    x_tx = S.tgt[bf][warp][0];   // written by the diagonal warp one phase ahead
-    x_ty = S.tgt[bf][warp][1];
-    x_tz = S.tgt[bf][warp][2];
+    // (computed here, not read from the diagonal warp's S.tgt: with one or two block columns this phase can run
+    //  before the diagonal warp has finished the previous group's epilogue and written the next coordinates)
+    x_tx = x_ty = x_tz = 0.0;
+    if (x_valid) gsm_target_coords(tg, tg.first + x_tt, x_tx, x_ty, x_tz);
     S.px[bf][warp][lane] = x_r.x;
     S.py[bf][warp][lane] = x_r.y;
     if (DIM3) S.pz[bf][warp][lane] = x_r.z;

@@ -493,6 +493,9 @@ STEADY = [
     ("uk", 3, 2, 32, (36, 30, 28), 25000, 1000, 25000, None),  # two right-hand-side block rows, slab
     ("ok", 2, None, 32, (256, 64), 2500, 0, None, 6.0),        # radius-limited: ragged and missing systems
     ("ok", 2, None, 32, (64, 48), 60000, 0, None, None),       # samples much denser than targets: pool overflow
+    ("sk", 2, None, 8, (256, 96), 5000, 0, None, None),        # one block column: the per-system pipelined kernel
+    ("ok", 2, None, 16, (256, 96), 30000, 0, None, None),      # dense samples, two block columns: pipelined kernel
+    ("uk", 3, 1, 8, (40, 36, 34), 20000, 0, None, None),       # 3-D, one block column, drift rows
 ]
 
 
