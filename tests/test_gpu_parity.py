@@ -496,6 +496,9 @@ STEADY = [
     ("sk", 2, None, 8, (256, 96), 5000, 0, None, None),        # one block column: the per-system pipelined kernel
     ("ok", 2, None, 16, (256, 96), 30000, 0, None, None),      # dense samples, two block columns: pipelined kernel
     ("uk", 3, 1, 8, (40, 36, 34), 20000, 0, None, None),       # 3-D, one block column, drift rows
+    ("ok", 2, None, 40, (128, 96), 6000, 0, None, None),       # 32 < k <= 64: several systems per persistent warp
+    ("uk", 3, 1, 64, (24, 24, 20), 30000, 0, None, None),
+    ("sk", 2, None, 64, (160, 64), 3000, 500, 9000, 7.5),      # k = 64, slab, radius-limited (ragged, missing)
 ]
 
 
