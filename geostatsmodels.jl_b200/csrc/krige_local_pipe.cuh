@@ -443,6 +443,7 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
   P4(0);
   bar_sync_sys();
   P5();
+  if (NBC <= 2) bar_sync_sys();
 
   int buf = 0;
   for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, buf ^= 1) {
@@ -602,6 +603,9 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
     TR(18);
     bar_sync_sys();        // next group's pooled covariances are complete
     P5();
+    // With one or two block columns the next group's hash inserts (P23) follow without a CTA-wide barrier in
+    // between (with four, the first hand-off lies in between): every warp must have released its entries first.
+    if (NBC <= 2) bar_sync_sys();
     TR(19);
   }
 }
