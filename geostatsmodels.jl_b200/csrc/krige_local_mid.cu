@@ -6,9 +6,13 @@
 // Differences from krige_local_shr.cuh / krige_local_pipe.cuh, which keep a 32 x 32 system in registers:
 //   * 36 + 8 blocks do not fit a warp's registers, so blocks live in shared memory (22.5 KB per system) and only
 //     the accumulator of the block being formed is in registers; the block loops are rolled (compact code);
-//   * warps are independent (no diagonal warp, no CTA barriers): the 8 x 8 diagonal blocks are inverted inside the
-//     warp (Gaussian elimination on [A | I] with shuffles);
+//   * TWO warps per system (the 22.5 KB per system bound the occupancy, not the warps): they split the assembly
+//     and the block rows of every column by parity and meet at one named barrier per column; no diagonal warp:
+//     the 8 x 8 diagonal blocks are inverted inside each warp (Gaussian elimination on [A | I] with shuffles),
+//     redundantly in both;
 //   * covariances are evaluated directly (no pooling across neighbouring targets).
+// One warp per system took 34 ms per 2^20 systems at k = 64, two take 30 ms (the redundant diagonal-block chain
+// dominates what is left).
 // It replaces the CTA-per-system SIMT kernel (krige_local_big.cu, kept as GSM_LOCAL_IMPL=big) as the k > 32 path.
 #include <algorithm>
 
@@ -17,7 +21,7 @@
 
 namespace {
 
-constexpr int MW = 4;                // system warps per CTA
+constexpr int MW = 4;                // systems per CTA (two warps each)
 constexpr int MKMAX = GSM_MAX_NEIGHBORS;   // 64
 constexpr int MNBC = MKMAX / 8;      // 8 block columns at most
 
@@ -74,7 +78,7 @@ struct MidWarp {
 };
 
 template <int NRB>
-__global__ void __launch_bounds__(MW * 32)
+__global__ void __launch_bounds__(MW * 64)
 local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant__ VarioDev v,
                        const __grid_constant__ ModelDev m, const __grid_constant__ gsm_cov::CovFast cf, int ncon,
                        int centered, const __grid_constant__ TargetsDev tg, int k, int minn,
@@ -84,7 +88,9 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  MidWarp<NRB>& S = reinterpret_cast<MidWarp<NRB>*>(smem_raw)[warp];
+  const int sys = warp >> 1, h = warp & 1;             // system of this CTA, half of the pair
+  MidWarp<NRB>& S = reinterpret_cast<MidWarp<NRB>*>(smem_raw)[sys];
+  auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + sys) : "memory"); };
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   const int nr = 2 + ncon;
   constexpr int NGB = NRB * (NRB + 1) / 2;
@@ -103,11 +109,11 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     X = make_double2(a0.x + a1.x, a0.y + a1.y);
   };
 
-  const long long nwarps = (long long)gridDim.x * MW;
-  for (long long tt = blockIdx.x * (long long)MW + warp; tt < tg.count; tt += nwarps) {
+  const long long nsys = (long long)gridDim.x * MW;
+  for (long long tt = blockIdx.x * (long long)MW + sys; tt < tg.count; tt += nsys) {
     int n = cnt[tt];
     if (n < minn || n <= 0) {
-      if (lane == 0) {
+      if (lane == 0 && h == 0) {
         out_mean[tt] = qnan;
         if (out_var) out_var[tt] = qnan;
         if (out_status) out_status[tt] = GSM_ST_MISSING;
@@ -119,28 +125,19 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     double tx, ty, tz;
     gsm_target_coords(tg, tg.first + tt, tx, ty, tz);
 
-    // ---- canonical neighbour order: ascending record position (rank by counting, two entries per lane) ----
-    __syncwarp();
-    const int p0 = lane < n ? pos[tt * (long long)k + lane] : 0x7fffffff;
-    const int p1 = lane + 32 < n ? pos[tt * (long long)k + lane + 32] : 0x7fffffff;
-    S.sp[lane] = p0;
-    S.sp[lane + 32] = p1;
-    __syncwarp();
-    int r0 = 0, r1 = 0;
-    for (int j = 0; j < n; ++j) {
-      const int pj = S.sp[j];
-      r0 += pj < p0 ? 1 : 0;
-      r1 += pj < p1 ? 1 : 0;
-    }
-    if (lane < n) {
+    // ---- canonical neighbour order: ascending record position (rank by counting; warp h takes entries 32h..) ----
+    pair_sync();                                        // the previous system of this pair is finished
+    const int e0 = 32 * h + lane;
+    const int p0 = e0 < n ? pos[tt * (long long)k + e0] : 0x7fffffff;
+    S.sp[e0] = p0;
+    pair_sync();
+    int r0 = 0;
+    for (int j = 0; j < n; ++j) r0 += S.sp[j] < p0 ? 1 : 0;
+    if (e0 < n) {
       const double4 r = b.rec[p0];
       S.px[r0] = r.x, S.py[r0] = r.y, S.pz[r0] = r.z, S.pv[r0] = r.w;
     }
-    if (lane + 32 < n) {
-      const double4 r = b.rec[p1];
-      S.px[r1] = r.x, S.py[r1] = r.y, S.pz[r1] = r.z, S.pv[r1] = r.w;
-    }
-    __syncwarp();
+    pair_sync();
     // drift scaling: centre at the target, scale by the neighbourhood radius (lower-set exponent tables)
     double ox = 0.0, oy = 0.0, oz = 0.0, isc = 1.0;
     if (centered) {
@@ -156,8 +153,10 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     }
 
     // ---- assemble the blocks (fragment layout); empty slots are identity rows / columns ----
+    int bcount = 0;
     for (int I = 0; I < nbc; ++I)
       for (int J = 0; J <= I; ++J) {
+        if (((bcount++) & 1) != h) continue;
         const int row = 8 * I + g, c0 = 8 * J + 2 * t;
         double e[2];
 #pragma unroll
@@ -178,6 +177,7 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     const int rbase = MNBC * (MNBC + 1) / 2;            // right-hand-side blocks: rbase + R * MNBC + J
     for (int R = 0; R < NRB; ++R)
       for (int J = 0; J < nbc; ++J) {
+        if (((bcount++) & 1) != h) continue;
         const int q = 8 * R + g, c0 = 8 * J + 2 * t;
         double e[2];
 #pragma unroll
@@ -198,16 +198,17 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         }
         put(S.blk[rbase + R * MNBC + J], make_double2(e[0], e[1]));
       }
-    __syncwarp();
+    pair_sync();
 
     // ---- left-looking blocked Cholesky, right-hand-side rows included; blocks are overwritten by L ----
+    // Column kb: both warps form the diagonal block and its inverse factor (redundantly), each takes the block
+    // rows of its parity; one barrier per column makes the new L blocks visible to the partner.
     bool bad = false;
     double2 Gacc[NGB];
 #pragma unroll
     for (int q = 0; q < NGB; ++q) Gacc[q] = make_double2(0.0, 0.0);
 #pragma unroll 1
     for (int kb = 0; kb < nbc; ++kb) {
-      // diagonal block
       double2 D = frag(S.blk[lowidx(kb, kb)]);
 #pragma unroll 1
       for (int j = 0; j < kb; ++j) {
@@ -215,9 +216,9 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         upd(D, L, L);
       }
       const double2 W = inv_chol_warp(D, g, t, bad);
-      // blocks below it, then the right-hand-side rows
 #pragma unroll 1
       for (int i = kb + 1; i < nbc + NRB; ++i) {
+        if ((i & 1) != h) continue;
         const bool rhs = i >= nbc;
         double* bi = rhs ? S.blk[rbase + (i - nbc) * MNBC + kb] : S.blk[lowidx(i, kb)];
         double2 C = frag(bi);
@@ -230,16 +231,19 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         panel(C, W);
         put(bi, C);
       }
-      __syncwarp();
-      // Schur blocks: G[r][q] -= L_Rr,kb L_Rq,kb'
+      pair_sync();
+      // Schur blocks: G[r][q] -= L_Rr,kb L_Rq,kb' (warp 0 of the pair)
+      if (h == 0) {
 #pragma unroll
-      for (int r = 0; r < NRB; ++r)
+        for (int r = 0; r < NRB; ++r)
 #pragma unroll
-        for (int q = 0; q <= r; ++q) {
-          const double2 X = frag(S.blk[rbase + r * MNBC + kb]), Y = frag(S.blk[rbase + q * MNBC + kb]);
-          upd(Gacc[r * (r + 1) / 2 + q], X, Y);
-        }
+          for (int q = 0; q <= r; ++q) {
+            const double2 X = frag(S.blk[rbase + r * MNBC + kb]), Y = frag(S.blk[rbase + q * MNBC + kb]);
+            upd(Gacc[r * (r + 1) / 2 + q], X, Y);
+          }
+      }
     }
+    if (h != 0) continue;                               // the epilogue belongs to warp 0 of the pair
 #pragma unroll
     for (int q = 0; q < NGB; ++q) put(S.G[q], Gacc[q]);
     const unsigned anybad = __ballot_sync(0xffffffffu, bad);
@@ -305,13 +309,13 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
 template <int NRB>
 int launch_mid(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered, const TargetsDev& tg, int k,
                int minn, const int* pos, const int* cnt, double* mean, double* var, unsigned char* status) {
-  const size_t smem = sizeof(MidWarp<NRB>) * MW;
+  const size_t smem = sizeof(MidWarp<NRB>) * MW;   // per system; two warps work on each
   auto kern = local_krige_mid_kernel<NRB>;
   GSM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = (int)std::max<size_t>(1, (227 * 1024) / (smem + 1024));
   const long long want = (tg.count + MW - 1) / MW;
   const int blocks = (int)std::min<long long>(want, 148LL * per_sm);
-  kern<<<blocks, MW * 32, smem, ctx->stream>>>(ctx->bins, v, m, gsm_cov::make_cov(v), ncon, centered, tg, k, minn, pos, cnt,
+  kern<<<blocks, MW * 64, smem, ctx->stream>>>(ctx->bins, v, m, gsm_cov::make_cov(v), ncon, centered, tg, k, minn, pos, cnt,
                                                mean, var, status);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
