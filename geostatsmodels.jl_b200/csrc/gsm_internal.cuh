@@ -30,6 +30,14 @@
 
 void gsm_set_error(gsm_ctx* ctx, const std::string& msg);
 
+// A pivot of the covariance block at or below GSM_PIVOT_RTOL * sill, or a pivot of the drift Schur complement at
+// or below GSM_SCHUR_RTOL times its own diagonal entry, marks the system singular (coincident samples, fewer points
+// than drift terms).  The reference's status(fit) = issuccess(bunchkaufman!(...)) (krig.jl:152) catches these
+// cases through exact zero pivots; here rounding can leave a pivot of a few ulps, which must not turn into an
+// unflagged garbage prediction.
+#define GSM_PIVOT_RTOL 1e-12
+#define GSM_SCHUR_RTOL 1e-11
+
 // ---------------------------------------------------------------------------------------------
 // device-side POD parameter blocks (passed by value as kernel arguments)
 // ---------------------------------------------------------------------------------------------

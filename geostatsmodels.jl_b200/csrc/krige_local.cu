@@ -127,7 +127,7 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     double d = gsm_shfl(a[j], j);
-    if (!(d > 0.0)) {
+    if (!(d > GSM_PIVOT_RTOL * v.sill)) {
       singular = true;
       d = 1.0;
     }
@@ -171,9 +171,11 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
     }
     // Cholesky of G (every lane redundantly, registers), solve G nu = g
 #pragma unroll
+    double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
+    for (int p0_ = 0; p0_ < NCON; ++p0_) gd0[p0_] = G[p0_ * NCON + p0_];
     for (int j = 0; j < NCON; ++j) {
       double d = G[j * NCON + j];
-      if (!(d > 0.0)) {
+      if (!(d > GSM_SCHUR_RTOL * gd0[j])) {
         singular = true;
         d = 1.0;
       }

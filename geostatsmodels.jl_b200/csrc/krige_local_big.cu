@@ -110,10 +110,11 @@ local_krige_big_kernel(BinsDev b, VarioDev v, ModelDev m, int ncon, int centered
   const int rows = n + nr;
   for (int j = 0; j < n; ++j) {
     const double d = A[j * BK_LD + j];
-    if (!(d > 0.0)) {
+    const bool okp = d > GSM_PIVOT_RTOL * v.sill;
+    if (!okp) {
       if (tid == 0) s_bad = 1;
     }
-    const double rs = rsqrt(d > 0.0 ? d : 1.0);
+    const double rs = rsqrt(okp ? d : 1.0);
     // A[r][c] -= l_r l_c for j < c <= r with l = A[.][j] * rs.  Column j is never read again (only the trailing
     // block is needed), so it is not scaled in place: one barrier per column.
     for (int c = j + 1 + cy; c < rows; c += 8) {
@@ -142,9 +143,11 @@ local_krige_big_kernel(BinsDev b, VarioDev v, ModelDev m, int ncon, int centered
         hw[p] = G(2 + p, 1);
         for (int q = 0; q <= p; ++q) Gs[p * ncon + q] = G(2 + p, 2 + q);
       }
+      double gd0[GSM_MAX_DRIFT];   // original diagonal: the singularity test is relative to it
+      for (int p0_ = 0; p0_ < ncon; ++p0_) gd0[p0_] = Gs[p0_ * ncon + p0_];
       for (int j = 0; j < ncon; ++j) {
         double d = Gs[j * ncon + j];
-        if (!(d > 0.0)) {
+        if (!(d > GSM_SCHUR_RTOL * gd0[j])) {
           singular = true;
           d = 1.0;
         }

@@ -113,7 +113,7 @@ __device__ __forceinline__ double cov_fast(const CovFast& c, double d2) {
 // upper part of `out` is zeroed once at kernel start and never touched).  Returns true if a pivot was
 // not positive.
 #define LIDX(i, j) ((i) * ((i) + 1) / 2 + (j))
-__device__ __forceinline__ bool diag_block(const double* __restrict__ blk, double* __restrict__ out) {
+__device__ __forceinline__ bool diag_block(const double* __restrict__ blk, double* __restrict__ out, double thr) {
   double a[36];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -123,7 +123,7 @@ __device__ __forceinline__ bool diag_block(const double* __restrict__ blk, doubl
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     double d = a[LIDX(j, j)];
-    if (!(d > 0.0)) {
+    if (!(d > thr)) {
       bad = true;
       d = 1.0;
     }
@@ -216,7 +216,7 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
         bar_sync(BAR_READY);
         TR(kb * 3 + 1);
         if (lane < SW) {
-          if (diag_block(&s_exin[lane * EXS], &s_exout[lane * EXS])) s_flag[lane] = 1;
+          if (diag_block(&s_exin[lane * EXS], &s_exout[lane * EXS], GSM_PIVOT_RTOL * v.sill)) s_flag[lane] = 1;
         }
         bar_arrive(BAR_DONE);
         TR(kb * 3 + 2);
@@ -465,9 +465,11 @@ local_krige_dmma_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
           for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, (tx - ox) * isc, (ty - oy) * isc, (tz - oz) * isc);
         }
 #pragma unroll
+        double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
+        for (int p0_ = 0; p0_ < NCON; ++p0_) gd0[p0_] = G[p0_ * NCON + p0_];
         for (int j = 0; j < NCON; ++j) {
           double d = G[j * NCON + j];
-          if (!(d > 0.0)) {
+          if (!(d > GSM_SCHUR_RTOL * gd0[j])) {
             singular = true;
             d = 1.0;
           }

@@ -41,7 +41,7 @@ __device__ __forceinline__ double rsqrt_m(double d) {
 // Warp-cooperative inverse Cholesky factor of an 8x8 SPD block in fragment layout (lane (g,t) owns A[g][2t],
 // A[g][2t+1]): Gaussian elimination without pivoting on [A | I] gives the unit-lower inverse M; scaling row g by
 // 1/sqrt(pivot g) turns it into W = L^-1 with A = L L'.
-__device__ __forceinline__ double2 inv_chol_warp(double2 a, int g, int t, bool& bad) {
+__device__ __forceinline__ double2 inv_chol_warp(double2 a, int g, int t, double thr, bool& bad) {
   double2 m = make_double2(g == 2 * t ? 1.0 : 0.0, g == 2 * t + 1 ? 1.0 : 0.0);
   double myrs = 1.0;
 #pragma unroll 1
@@ -51,7 +51,7 @@ __device__ __forceinline__ double2 inv_chol_warp(double2 a, int g, int t, bool& 
     const double arj = gsm_shfl(ac, g * 4 + (j >> 1));    // A[g][j]
     const double pj0 = gsm_shfl(a.x, j * 4 + t), pj1 = gsm_shfl(a.y, j * 4 + t);   // pivot row of A
     const double mj0 = gsm_shfl(m.x, j * 4 + t), mj1 = gsm_shfl(m.y, j * 4 + t);   // pivot row of M
-    if (!(d > 0.0)) {
+    if (!(d > thr)) {
       bad = true;
       d = 1.0;
     }
@@ -215,7 +215,7 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         const double2 L = frag(S.blk[lowidx(kb, j)]);
         upd(D, L, L);
       }
-      const double2 W = inv_chol_warp(D, g, t, bad);
+      const double2 W = inv_chol_warp(D, g, t, GSM_PIVOT_RTOL * v.sill, bad);
 #pragma unroll 1
       for (int i = kb + 1; i < nbc + NRB; ++i) {
         if ((i & 1) != h) continue;
@@ -271,9 +271,11 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
           hw[p] = Gm(2 + p, 1);
           for (int q = 0; q <= p; ++q) Gs[p * ncon + q] = Gm(2 + p, 2 + q);
         }
+        double gd0[GSM_MAX_DRIFT];   // original diagonal: the singularity test is relative to it
+        for (int p0_ = 0; p0_ < ncon; ++p0_) gd0[p0_] = Gs[p0_ * ncon + p0_];
         for (int j = 0; j < ncon; ++j) {
           double d = Gs[j * ncon + j];
-          if (!(d > 0.0)) {
+          if (!(d > GSM_SCHUR_RTOL * gd0[j])) {
             singular = true;
             d = 1.0;
           }

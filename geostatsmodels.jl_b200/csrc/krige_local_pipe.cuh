@@ -104,7 +104,7 @@ __device__ __forceinline__ double cov_fast(const CovFast& c, double d2) {
 
 // thread-per-block Cholesky + inverse of an 8x8 SPD block (see krige_local_dmma.cu)
 #define LIDX(i, j) ((i) * ((i) + 1) / 2 + (j))
-__device__ __forceinline__ bool diag_block(const double* __restrict__ blk, double* __restrict__ out) {
+__device__ __forceinline__ bool diag_block(const double* __restrict__ blk, double* __restrict__ out, double thr) {
   double a[36];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -114,7 +114,7 @@ __device__ __forceinline__ bool diag_block(const double* __restrict__ blk, doubl
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     double d = a[LIDX(j, j)];
-    if (!(d > 0.0)) {
+    if (!(d > thr)) {
       bad = true;
       d = 1.0;
     }
@@ -219,7 +219,7 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
         bar_sync(BAR_READY);
         TR(kb * 3 + 1);
         if (lane < SW) {
-          if (diag_block(&S.exin[lane * EXS], &S.exout[lane * EXS])) S.flag[lane] = 1;
+          if (diag_block(&S.exin[lane * EXS], &S.exout[lane * EXS], GSM_PIVOT_RTOL * v.sill)) S.flag[lane] = 1;
         }
         bar_arrive(BAR_DONE);
         TR(kb * 3 + 2);
@@ -258,9 +258,11 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
             for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, tx, ty, tz);
           }
 #pragma unroll
+          double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
+          for (int p0_ = 0; p0_ < NCON; ++p0_) gd0[p0_] = Gs[p0_ * NCON + p0_];
           for (int j = 0; j < NCON; ++j) {
             double d = Gs[j * NCON + j];
-            if (!(d > 0.0)) {
+            if (!(d > GSM_SCHUR_RTOL * gd0[j])) {
               singular = true;
               d = 1.0;
             }

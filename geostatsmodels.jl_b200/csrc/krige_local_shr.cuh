@@ -117,7 +117,7 @@ __device__ __forceinline__ double cov_fast(const CovFast& c, double d2) {
 
 // thread-per-block Cholesky + inverse of an 8x8 SPD block (diagonal warp)
 #define LIDX(i, j) ((i) * ((i) + 1) / 2 + (j))
-__device__ __forceinline__ bool diag_block(const double* __restrict__ blk, double* __restrict__ out) {
+__device__ __forceinline__ bool diag_block(const double* __restrict__ blk, double* __restrict__ out, double thr) {
   double a[36];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -127,7 +127,7 @@ __device__ __forceinline__ bool diag_block(const double* __restrict__ blk, doubl
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     double d = a[LIDX(j, j)];
-    if (!(d > 0.0)) {
+    if (!(d > thr)) {
       bad = true;
       d = 1.0;
     }
@@ -308,7 +308,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         }
       }
       if (in != nullptr) {
-        if (diag_block(in, out)) *badp = 1;
+        if (diag_block(in, out, GSM_PIVOT_RTOL * v.sill)) *badp = 1;
       }
     };
     auto epilogue = [&](int j) __attribute__((always_inline)) {
@@ -349,9 +349,11 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
             for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, tx, ty, tz);
           }
 #pragma unroll
+          double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
+          for (int p0_ = 0; p0_ < NCON; ++p0_) gd0[p0_] = Gs[p0_ * NCON + p0_];
           for (int j2 = 0; j2 < NCON; ++j2) {
             double d = Gs[j2 * NCON + j2];
-            if (!(d > 0.0)) {
+            if (!(d > GSM_SCHUR_RTOL * gd0[j2])) {
               singular = true;
               d = 1.0;
             }
