@@ -623,3 +623,19 @@ def test_full_size_north_star_3d(gsm, oracle):
         o._dom_absmax = orig
     assert (st == 0).all()
     assert np.allclose(mu1[idx], mu, rtol=RTOL, atol=ATOL) and np.allclose(var1[idx], var, rtol=RTOL, atol=ATOL)
+
+
+def test_randomised_parity_sweep(gsm, oracle):
+    """200 random neighbourhood cases (model, variogram, dimension, k up to 64, grid shape, slab, radius,
+    minneighbors, coincident samples) against the C oracle: tools/fuzz_parity.py."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_parity", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_parity.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    bad = []
+    for seed in range(5000, 5200):
+        ok, desc = fz.one(seed)
+        if not ok:
+            bad.append(desc)
+    assert not bad, bad

@@ -8,10 +8,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry
 
-ap = argparse.ArgumentParser()
-ap.add_argument("--cases", type=int, default=60)
-ap.add_argument("--seed", type=int, default=None)
-args = ap.parse_args()
 gsm = entry.load_package()
 o = entry.load_oracle()
 import gsm_oracle_c as oc
@@ -75,7 +71,12 @@ def one(seed):
     # singular systems (duplicates, too few points for the drift) may be flagged on either side only when the
     # matrix is numerically singular; compare where both are fine, and require the flags to agree on "missing"
     both = ~bad_o & ~bad_g
-    tol = 1e-10 if kind != "uk" else 1e-6   # UK: the reference formulation itself loses digits
+    # UK: the reference formulation (raw monomials in a saddle matrix) itself loses digits, the more the closer the
+    # neighbourhood is to having as many points as monomials (the GPU side is the accurate one,
+    # tests/test_gpu_parity.py::test_uk_quadratic_3d_against_exact_arithmetic)
+    tol = 1e-10
+    if kind == "uk":
+        tol = 1e-6 if (k >= 3 * ncon and nbh is None) else 1e-3   # (a radius can leave barely more points than monomials)
     # Numerically singular systems (coincident samples, barely determined drifts): the oracle flags exact zero
     # pivots only, the GPU everything below GSM_PIVOT_RTOL / GSM_SCHUR_RTOL -- it may flag more, within reason
     allow = 0.15 if (dups or (kind == "uk" and nbh is not None)) else 0.02
@@ -87,17 +88,22 @@ def one(seed):
     return ok, desc
 
 
-seeds = [args.seed] if args.seed is not None else list(range(1000, 1000 + args.cases))
-t0 = time.time()
-nfail = 0
-for sd in seeds:
-    try:
-        ok, desc = one(sd)
-    except Exception as ex:
-        ok, desc = False, f"seed {sd}: EXCEPTION {ex!r}"
-    if not ok:
-        nfail += 1
-        print("FAIL", desc, flush=True)
-    elif args.seed is not None:
-        print("ok  ", desc)
-print(f"{len(seeds) - nfail} of {len(seeds)} cases agree with the oracle ({time.time() - t0:.0f} s)")
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=60)
+    ap.add_argument("--seed", type=int, default=None)
+    args = ap.parse_args()
+    seeds = [args.seed] if args.seed is not None else list(range(1000, 1000 + args.cases))
+    t0 = time.time()
+    nfail = 0
+    for sd in seeds:
+        try:
+            ok, desc = one(sd)
+        except Exception as ex:
+            ok, desc = False, f"seed {sd}: EXCEPTION {ex!r}"
+        if not ok:
+            nfail += 1
+            print("FAIL", desc, flush=True)
+        elif args.seed is not None:
+            print("ok  ", desc)
+    print(f"{len(seeds) - nfail} of {len(seeds)} cases agree with the oracle ({time.time() - t0:.0f} s)")
