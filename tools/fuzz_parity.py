@@ -44,6 +44,12 @@ def one(seed):
         minn = max(minn, ncon + 3)
     og = o.Grid(tuple(0.0 for _ in dims), tuple(float(e / d) for e, d in zip(ext, dims)), dims)
     grid = gsm.CartesianGrid(tuple(0.0 for _ in dims), tuple(float(e) for e in ext), dims=dims)
+    if rng.random() < 0.25:   # explicit points instead of a grid (the per-system kernels; the order carries no locality)
+        P = rng.uniform(-0.05, 1.05, size=(min(M, 4000), dim)) * ext
+        og, grid = P, gsm.PointSet(P)
+        first = min(first, P.shape[0] - 1)
+        count = None if count is None else max(1, min(count, P.shape[0] - first))
+        dims = ("points", P.shape[0])
     tab = gsm.georef({"z": z}, gsm.PointSet(X))
     kw = dict(maxneighbors=k, minneighbors=minn, first=first)
     desc = f"seed {seed}: {kind} vk={vk} dim={dim} k={k} dims={dims} n={n} first={first} count={count} nbh={nbh} minn={minn} deg={deg}"
