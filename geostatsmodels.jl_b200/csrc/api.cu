@@ -494,7 +494,12 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
     int* d_pos = (int*)ctx->nbr_pos.p;
     int* d_cnt = d_cnt_all + off;
     cudaEvent_t a = et.mark(st);
-    GSM_CHECK(gsm_launch_knn(ctx, tc, maxn, opts->radius, d_pos, d_cnt));
+    const bool fused_idw = mode == 2 && !onbr.dev;   // local IDW without neighbour lists: predict inside the search
+    if (fused_idw)
+      GSM_CHECK(gsm_launch_knn_idw(ctx, tc, maxn, opts->radius, exponent, minn, d_cnt, omean.dev + off,
+                                   ostat.dev ? ostat.dev + off : nullptr));
+    else
+      GSM_CHECK(gsm_launch_knn(ctx, tc, maxn, opts->radius, d_pos, d_cnt));
     cudaEvent_t bq = et.mark(st);
     if (onbr.dev) {
       GSM_CHECK(gsm_launch_sort_lists(ctx, tc, maxn, d_pos, d_cnt));   // lists are promised ascending by (d2, row)
@@ -503,7 +508,7 @@ static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const g
     if (mode == 1) {
       GSM_CHECK(gsm_launch_local_krige(ctx, vd, md, tc, maxn, minn, d_pos, d_cnt, omean.dev + off,
                                        ovar.dev ? ovar.dev + off : nullptr, ostat.dev ? ostat.dev + off : nullptr));
-    } else if (mode == 2) {
+    } else if (mode == 2 && !fused_idw) {
       GSM_CHECK(gsm_launch_idw_local(ctx, exponent, tc, maxn, minn, d_pos, d_cnt, omean.dev + off,
                                      ostat.dev ? ostat.dev + off : nullptr));
     }

@@ -36,7 +36,7 @@ void gsm_set_error(gsm_ctx* ctx, const std::string& msg);
 // cases through exact zero pivots; here rounding can leave a pivot of a few ulps, which must not turn into an
 // unflagged garbage prediction.
 #define GSM_PIVOT_RTOL 1e-12
-#define GSM_SCHUR_RTOL 1e-11
+#define GSM_SCHUR_RTOL 1e-13
 
 // ---------------------------------------------------------------------------------------------
 // device-side POD parameter blocks (passed by value as kernel arguments)
@@ -143,6 +143,8 @@ bool gsm_is_device_ptr(const void* p);
 // ---------------------------------------------------------------------------------------------
 int gsm_build_bins(gsm_ctx* ctx);
 int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt);
+int gsm_launch_knn_idw(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, double exponent, int minneighbors,
+                       int* d_cnt, double* d_mean, unsigned char* d_status);
 int gsm_launch_sort_lists(gsm_ctx* ctx, const TargetsDev& tg, int k, int* d_pos, const int* d_cnt);
 int gsm_launch_nbr_to_rows(gsm_ctx* ctx, const int* d_pos, long long total, int* d_rows);
 int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k,

@@ -6,34 +6,14 @@
 // coalesced loads and consumed as warp-wide broadcasts.  N*M pair interactions on O(N+M) bytes: the
 // kernel is FP64-pipe bound, not HBM bound.  Local form: O(k) work per target on gathered records.
 #include "gsm_internal.cuh"
+#include "idw_weight.cuh"
 
 namespace {
 
 constexpr int IDW_THREADS = 128;
 constexpr int IDW_TILE = 512;
 
-// 1/d, d > 0 finite: hardware seed + two Newton steps (full double precision, no slow-path branch)
-__device__ __forceinline__ double idw_rcp(double d) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  y = fma(y, fma(-d, y, 1.0), y);
-  y = fma(y, fma(-d, y, 1.0), y);
-  return y;
-}
-
-// EXPMODE: 1 -> e == 1, 2 -> e == 2, 3 -> other positive integer, 0 -> real exponent
-template <int EXPMODE>
-__device__ __forceinline__ double idw_weight(double d2, double e, int ei) {
-  if (EXPMODE == 2) return (d2 > 1e-290 && d2 < 1e290) ? idw_rcp(d2) : 1.0 / d2;
-  if (EXPMODE == 1) return 1.0 / sqrt(d2);
-  const double d = sqrt(d2);
-  if (EXPMODE == 3) {
-    double p = d;
-    for (int i = 1; i < ei; ++i) p *= d;
-    return 1.0 / p;
-  }
-  return 1.0 / pow(d, e);
-}
+using gsm_idww::idw_weight;
 
 // IDW_TPB targets per CTA, IDW_SPLIT threads per target: thread (target, q) takes the samples i = q mod IDW_SPLIT
 // of every tile, so a 256 x 256 grid (config C1) still fills the SMs; the IDW_SPLIT partial sums of a target are
@@ -148,13 +128,7 @@ idw_local_kernel(BinsDev b, TargetsDev tg, int k, int minn, double e, int ei, co
   if (status) status[t] = GSM_ST_OK;
 }
 
-int exp_mode(double e, int& ei) {
-  ei = (int)e;
-  if (e == 1.0) return 1;
-  if (e == 2.0) return 2;
-  if (e > 0 && e == (double)ei && ei <= 64) return 3;
-  return 0;
-}
+using gsm_idww::exp_mode;
 
 }  // namespace
 

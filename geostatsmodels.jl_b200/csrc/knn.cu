@@ -15,6 +15,7 @@
 // Output per target: positions into the cell-sorted record array in heap order (a deterministic
 // function of the inputs); sort_lists_kernel orders them ascending when the caller asks for lists.
 #include "gsm_internal.cuh"
+#include "idw_weight.cuh"
 
 namespace {
 
@@ -75,8 +76,18 @@ __device__ __forceinline__ void sift_up(Heap& hp, int i, double d, int p, const 
   hp.P(i) = p;
 }
 
+// Local IDW fused into the search (gsm_idw with a neighbourhood, models.jl:162-184 with idw.jl:59-89): the weights
+// only need the k selected (d2, value) pairs, which the heap already holds, so nothing but the prediction leaves.
+struct KnnIdw {
+  int on;                 // 0: emit the neighbour lists; 1: emit IDW predictions
+  int mode, ei, minn;     // exponent class (gsm_idww::exp_mode), integer exponent, minneighbors
+  double e;
+  double* mean;
+  unsigned char* status;
+};
+
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long row0, int ntx, int nty,
+knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long row0, int ntx, int nty, KnnIdw idw,
            int* __restrict__ out_pos, int* __restrict__ out_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Heap hp;
@@ -251,6 +262,38 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
     }
     prev_worst = (cnt == k) ? worst : inf;
 
+    if (idw.on) {
+      // ---- fused local IDW over the selected neighbours, in heap order (the order idw_local_kernel would see) ----
+      double sw = 0.0, swz = 0.0, hitv = 0.0;
+      int nkeep = 0, hitrow = 0x7fffffff;
+      for (int i = 0; i < cnt; ++i) {
+        const double d2 = hp.D(i);
+        if (radius > 0.0 && !(__dsqrt_rn(d2) <= radius)) continue;
+        nkeep++;
+        const int q = hp.P(i);
+        const double val = rec[q].w;
+        if (d2 > 0.0) {
+          const double w = gsm_idww::idw_weight_rt(idw.mode, d2, idw.e, idw.ei);
+          sw += w;
+          swz = fma(w, val, swz);
+        } else {   // exact hit: the FIRST such sample of the reference's ascending (d2, row) list = lowest row
+          const int rw = sidx[q];
+          if (rw < hitrow) {
+            hitrow = rw;
+            hitv = val;
+          }
+        }
+      }
+      out_cnt[t] = nkeep;
+      if (nkeep < idw.minn || nkeep <= 0) {
+        idw.mean[t] = __longlong_as_double(0x7ff8000000000000LL);
+        if (idw.status) idw.status[t] = GSM_ST_MISSING;
+      } else {
+        idw.mean[t] = hitrow != 0x7fffffff ? hitv : swz / sw;
+        if (idw.status) idw.status[t] = GSM_ST_OK;
+      }
+      continue;
+    }
     // ---- emit (heap order); KBallSearch keeps neighbours with distance <= radius (models.jl:158) ----
     int* o = out_pos + t * (long long)k;
     int nkeep = 0;
@@ -305,7 +348,8 @@ __global__ void pos_to_rows_kernel(const int* __restrict__ pos, long long total,
 
 }  // namespace
 
-int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt) {
+static int launch_knn_impl(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, const KnnIdw& idw, int* d_pos,
+                           int* d_cnt) {
   if (tg.count <= 0) return GSM_OK;
   size_t smem = (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int));
   GSM_CUDA(ctx, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -328,11 +372,28 @@ int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int
       blocks = (long long)ntx * nty * (z_hi / 2 - row0 + 1);
     }
   }
-  knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, tiled, row0, ntx, nty, d_pos,
-                                                                  d_cnt);
+  knn_kernel<<<(unsigned)blocks, KNN_THREADS, smem, ctx->stream>>>(ctx->bins, tg, k, radius, tiled, row0, ntx, nty, idw,
+                                                                  d_pos, d_cnt);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
   return GSM_OK;
+}
+
+int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt) {
+  KnnIdw off{};
+  return launch_knn_impl(ctx, tg, k, radius, off, d_pos, d_cnt);
+}
+
+int gsm_launch_knn_idw(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, double exponent, int minneighbors,
+                       int* d_cnt, double* d_mean, unsigned char* d_status) {
+  KnnIdw f{};
+  f.on = 1;
+  f.mode = gsm_idww::exp_mode(exponent, f.ei);
+  f.e = exponent;
+  f.minn = minneighbors;
+  f.mean = d_mean;
+  f.status = d_status;
+  return launch_knn_impl(ctx, tg, k, radius, f, nullptr, d_cnt);
 }
 
 int gsm_launch_sort_lists(gsm_ctx* ctx, const TargetsDev& tg, int k, int* d_pos, const int* d_cnt) {
