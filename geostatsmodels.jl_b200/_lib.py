@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gsm_abi_version", "gsm_create", "gsm_destroy", "gsm_last_error", "gsm_get_timings", "gsm_get_summary", "gsm_synchronize",
     "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_set_samples_scaled", "gsm_knn", "gsm_local_krige",
     "gsm_global_krige_fit", "gsm_global_krige_status", "gsm_global_krige_predict", "gsm_global_krige_free",
-    "gsm_idw", "gsm_measure_fp64_peak",
+    "gsm_idw", "gsm_nn", "gsm_measure_fp64_peak",
 ]
 
 
@@ -105,6 +105,7 @@ def load():
     lib.gsm_global_krige_predict.argtypes = [vp, P(Targets), vp, vp]
     lib.gsm_global_krige_free.argtypes = [vp]
     lib.gsm_idw.argtypes = [vp, dbl, P(Targets), P(NeighborOpts), vp, vp]
+    lib.gsm_nn.argtypes = [vp, P(Targets), vp]
     lib.gsm_measure_fp64_peak.argtypes = [vp, P(dbl), P(dbl)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
@@ -345,6 +346,13 @@ class Context:
         self._check(self._lib.gsm_idw(self._h, float(exponent), C.byref(targets),
                                       C.byref(o) if o is not None else None, _ptr(mean), _ptr(status)))
         return mean, status
+
+    def nn(self, targets: Targets, out=None):
+        """value of the nearest sample for every target (gsm_nn)"""
+        M = self.target_count(targets)
+        val = _pool.empty(M, np.float64) if out is None else out
+        self._check(self._lib.gsm_nn(self._h, C.byref(targets), _ptr(val)))
+        return val
 
     def global_fit(self, vario: Variogram, model: Model):
         h = C.c_void_p()

@@ -22,7 +22,7 @@ from . import _lib
 
 __all__ = [
     "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "PointSet", "CartesianGrid", "GeoTable",
-    "georef", "IDW", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
+    "georef", "IDW", "NN", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
     "predict", "predictprob", "status", "fitpredict", "default_context", "set_default_device",
 ]
 
@@ -178,6 +178,16 @@ class IDW:
 
     def _range(self):
         return math.inf  # Base.range(::GeoStatsModel) = Inf (models.jl:22)
+
+
+@dataclass(frozen=True)
+class NN:
+    """NN(distance=Euclidean()) (nn.jl:14-24): the value of the nearest sample."""
+    distance: str = "euclidean"
+
+    def _range(self):
+        return math.inf
+
 
 
 class _KrigingModel:
@@ -424,7 +434,12 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     if neighborhood is not None:
         radius = alpha * float(neighborhood)           # sneigh = alpha * neigh (models.jl:281), ball radius
     M = _lib.Context.target_count(t)
-    if isinstance(model, IDW):
+    if isinstance(model, NN):
+        if prob:
+            raise NotImplementedError("NN with prob=true (Dirac) is not claimed by the GPU path")
+        # nearest of the k nearest = nearest of all: the neighbourhood options do not change the result (nn.jl:47-54)
+        col = ctx.nn(t, out=out.get("mean"))
+    elif isinstance(model, IDW):
         if prob:
             raise NotImplementedError("IDW with prob=true is not claimed by the GPU path")
         if neighbors:

@@ -570,6 +570,40 @@ int gsm_local_krige(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_model* m
   return run_local(ctx, 1, vario, model, 0.0, targets, opts, out_mean, out_var, out_status, out_nbr, nullptr);
 }
 
+int gsm_nn(gsm_ctx* ctx, const gsm_targets* targets, double* out_value) {
+  if (!ctx) return GSM_ERR_INVALID;
+  if (!out_value) {
+    gsm_set_error(ctx, "out_value is required");
+    return GSM_ERR_INVALID;
+  }
+  if (ctx->n <= 0) {
+    gsm_set_error(ctx, "no samples: call gsm_set_samples first");
+    return GSM_ERR_NO_SAMPLES;
+  }
+  DeviceGuard g(ctx->device);
+  ctx->tim = gsm_timings{};
+  EventTimer et;
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t e0 = et.mark(st);
+  TargetsDev td{};
+  long long M = 0;
+  GSM_CHECK(make_targets(ctx, targets, td, M));
+  cudaEvent_t e1 = et.mark(st);
+  OutBuf<double> oval;
+  GSM_CHECK(oval.init(ctx, out_value, ctx->out_mean, M));
+  GSM_CHECK(gsm_reserve(ctx, ctx->nbr_cnt, (size_t)std::max<long long>(M, 1) * sizeof(int)));
+  GSM_CHECK(gsm_launch_knn_nearest(ctx, td, (int*)ctx->nbr_cnt.p, oval.dev));
+  cudaEvent_t e2 = et.mark(st);
+  GSM_CHECK(oval.download(ctx, 0, M, st));
+  cudaEvent_t e3 = et.mark(st);
+  GSM_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->tim.h2d_ms = EventTimer::ms(e0, e1);
+  ctx->tim.knn_ms = EventTimer::ms(e1, e2);
+  ctx->tim.d2h_ms = EventTimer::ms(e2, e3);
+  ctx->tim.total_ms = EventTimer::ms(e0, e3);
+  return GSM_OK;
+}
+
 int gsm_idw(gsm_ctx* ctx, double exponent, const gsm_targets* targets, const gsm_neighbor_opts* opts,
             double* out_mean, uint8_t* out_status) {
   if (!ctx) return GSM_ERR_INVALID;

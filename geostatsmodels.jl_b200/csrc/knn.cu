@@ -262,6 +262,16 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
     }
     prev_worst = (cnt == k) ? worst : inf;
 
+    if (idw.on && idw.mode < 0) {
+      // ---- NN model (nn.jl:47-54): the nearest sample's value; among equidistant samples the lowest row ----
+      int best = -1;
+      for (int i = 0; i < cnt; ++i)
+        if (best < 0 || key_less(hp.D(i), hp.P(i), hp.D(best), hp.P(best), sidx)) best = i;
+      idw.mean[t] = best >= 0 ? rec[hp.P(best)].w : __longlong_as_double(0x7ff8000000000000LL);
+      if (idw.status) idw.status[t] = best >= 0 ? GSM_ST_OK : GSM_ST_MISSING;
+      out_cnt[t] = cnt;
+      continue;
+    }
     if (idw.on) {
       // ---- fused local IDW over the selected neighbours, in heap order (the order idw_local_kernel would see) ----
       double sw = 0.0, swz = 0.0, hitv = 0.0;
@@ -394,6 +404,15 @@ int gsm_launch_knn_idw(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius,
   f.mean = d_mean;
   f.status = d_status;
   return launch_knn_impl(ctx, tg, k, radius, f, nullptr, d_cnt);
+}
+
+int gsm_launch_knn_nearest(gsm_ctx* ctx, const TargetsDev& tg, int* d_cnt, double* d_value) {
+  KnnIdw f{};
+  f.on = 1;
+  f.mode = -1;
+  f.minn = 1;
+  f.mean = d_value;
+  return launch_knn_impl(ctx, tg, 1, 0.0, f, nullptr, d_cnt);
 }
 
 int gsm_launch_sort_lists(gsm_ctx* ctx, const TargetsDev& tg, int k, int* d_pos, const int* d_cnt) {

@@ -183,6 +183,10 @@ GSM_API int gsm_global_krige_free(gsm_fit* fit);
 GSM_API int gsm_idw(gsm_ctx* ctx, double exponent, const gsm_targets* targets, const gsm_neighbor_opts* opts,
             double* out_mean, uint8_t* out_status);
 
+/* ---- NN (nn.jl:47-54): value of the nearest sample (ties: the lowest sample row, the order a stable sortperm of the
+ * distances gives).  SURVEY section 8(f) "next" row; missing values are not claimed. */
+GSM_API int gsm_nn(gsm_ctx* ctx, const gsm_targets* targets, double* out_value);
+
 /* ---- measurement helper: sustained FP64 FMA throughput of this device in TFLOP/s (roofline peak) */
 GSM_API int gsm_measure_fp64_peak(gsm_ctx* ctx, double* out_dfma_tflops, double* out_dmma_tflops);
 

@@ -321,6 +321,17 @@ class IDWModel:
     exponent: float = 1.0
 
 
+@dataclass(frozen=True)
+class NNModel:
+    """NN (src/nn.jl:47-54): z[sortperm(distances)][1]; the sort is stable, so equidistant samples resolve to the
+    lowest row -- the same (d2, row) order as the neighbour search."""
+
+
+def nn_predict(X: np.ndarray, z: np.ndarray, x0: np.ndarray) -> float:
+    d2 = sqdist_keys(X, x0)
+    return float(z[np.lexsort((np.arange(X.shape[0]), d2))[0]])
+
+
 def _targets(dom, first=0, count=None) -> np.ndarray:
     if isinstance(dom, Grid):
         return dom.centroids(first, count)
@@ -380,6 +391,9 @@ def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, 
                     var[j] = v
             if not ks.status():
                 status[:] = 2
+        elif isinstance(smodel, NNModel):
+            for j in range(M):
+                mean[j] = nn_predict(sX, z, sT[j])
         else:
             for j in range(M):
                 mean[j] = idw_predict(sX, z, sT[j], smodel.exponent)
@@ -389,6 +403,8 @@ def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, 
 
 
 def _predict_one(smodel, Xn, zn, x0):
+    if isinstance(smodel, NNModel):
+        return nn_predict(Xn, zn, x0), 0.0, True
     if isinstance(smodel, KrigingModel):
         ks = KrigingSystem(smodel, Xn, zn)
         mu, v = ks.predict(x0)

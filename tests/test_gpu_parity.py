@@ -639,3 +639,21 @@ def test_randomised_parity_sweep(gsm, oracle):
         if not ok:
             bad.append(desc)
     assert not bad, bad
+
+
+def test_nn_model_matches_oracle(gsm, oracle):
+    """NN (nn.jl:47-54): the nearest sample's value, ties to the lowest row."""
+    o = oracle
+    rng = np.random.default_rng(12)
+    for dim, dims in ((2, (37, 23)), (3, (11, 9, 7))):
+        X = np.floor(rng.uniform(0, 30, size=(900, dim)))          # lattice samples: many exact distance ties
+        z = rng.standard_normal(900)
+        grid = gsm.CartesianGrid(tuple(0.0 for _ in dims), tuple(30.0 for _ in dims), dims=dims)
+        og = o.Grid(tuple(0.0 for _ in dims), tuple(30.0 / d for d in dims), dims)
+        got = gsm.fitpredict(gsm.NN(), gsm.georef({"z": z}, gsm.PointSet(X)), grid).z
+        ref, _, _ = o.fitpredict(o.NNModel(), X, z, og, neighbors=False)
+        assert np.array_equal(got, ref)
+        P = rng.uniform(-3, 33, size=(500, dim))
+        got = gsm.fitpredict(gsm.NN(), gsm.georef({"z": z}, gsm.PointSet(X)), gsm.PointSet(P)).z
+        ref, _, _ = o.fitpredict(o.NNModel(), X, z, P, neighbors=False)
+        assert np.array_equal(got, ref)
