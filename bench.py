@@ -248,6 +248,22 @@ def run_ours(args):
                 "total_ms": t_bins["total_ms"] + t["total_ms"], "launches": t_bins["launches"] + t["launches"]}
 
     fp64_dfma, fp64_dmma = ctx.measure_fp64_peak()
+    # third opinion on the FP64 peak: the library DGEMM (cuBLAS through torch; plumbing, not on the timed path)
+    fp64_cublas = 0.0
+    try:
+        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        torch.matmul(a, b)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        fp64_cublas = 5 * 2 * 4096.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b
+    except Exception:
+        pass
 
     # ---- value: device-resident --------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -312,7 +328,7 @@ def run_ours(args):
         kern_ms = solve_ms - index_ms
         solve_launch_ms = kern_ms / (steps * max(1, -(-M // (1 << 20))))
         solve_tflops = fpp * M * steps / (kern_ms * 1e-3) / 1e12
-        peak = max(fp64_dfma, fp64_dmma)
+        peak = max(fp64_dfma, fp64_dmma, fp64_cublas)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -334,8 +350,9 @@ def run_ours(args):
                                    "nccl_broadcast_once": bcast_ms},
             "roofline": {"bound": "fp64", "kernel": "local_krige_shr_kernel<1,false,4> (gather + shared-factor blocked Cholesky + solve)",
                          "achieved": solve_tflops, "peak": peak, "unit": "TFLOP/s", "frac": solve_tflops / peak,
-                         "peak_source": "measured in this run (gsm_measure_fp64_peak: DFMA %.1f, DMMA m8n8k4 %.1f TFLOP/s);"
-                                        " MEASURED_PEAKS.json has no FP64 entry" % (fp64_dfma, fp64_dmma),
+                         "peak_source": "measured in this run (gsm_measure_fp64_peak: DFMA %.1f, DMMA m8n8k4 %.1f TFLOP/s; "
+                                        "cuBLAS DGEMM 4096^3 %.1f TFLOP/s); MEASURED_PEAKS.json has no FP64 entry"
+                                        % (fp64_dfma, fp64_dmma, fp64_cublas),
                          "flops_per_prediction": fpp, "launch_ms": solve_launch_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (2^20 systems) from the
                          # `ncu --set full` capture summarised in profiles/r01_knn_index_local_krige_shr_ncu_summary.txt;
