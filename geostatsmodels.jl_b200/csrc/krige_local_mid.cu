@@ -6,13 +6,13 @@
 // Differences from krige_local_shr.cuh / krige_local_pipe.cuh, which keep a 32 x 32 system in registers:
 //   * 36 + 8 blocks do not fit a warp's registers, so blocks live in shared memory (22.5 KB per system) and only
 //     the accumulator of the block being formed is in registers; the block loops are rolled (compact code);
-//   * TWO warps per system (the 22.5 KB per system bound the occupancy, not the warps): they split the assembly
-//     and the block rows of every column by parity and meet at one named barrier per column; no diagonal warp:
-//     the 8 x 8 diagonal blocks are inverted inside each warp (Gaussian elimination on [A | I] with shuffles),
-//     redundantly in both;
+//   * TWO warps per system (the 22.5 KB per system bound the occupancy, not the warps) that meet at one named
+//     barrier per column: warp A runs the serial chain one column ahead (block row kb+1 -> next diagonal block ->
+//     its inverse factor, Gaussian elimination on [A | I] with shuffles inside the warp), warp B does every other
+//     block row of the column and the Schur blocks; the assembly is split by parity;
 //   * covariances are evaluated directly (no pooling across neighbouring targets).
-// One warp per system took 34 ms per 2^20 systems at k = 64, two take 30 ms (the redundant diagonal-block chain
-// dominates what is left).
+// One warp per system took 34 ms per 2^20 systems at k = 64, two with look-ahead take 26 ms (the chain of eight
+// diagonal-block inversions per system is what is left).
 // It replaces the CTA-per-system SIMT kernel (krige_local_big.cu, kept as GSM_LOCAL_IMPL=big) as the k > 32 path.
 #include <algorithm>
 
@@ -70,11 +70,13 @@ __device__ __forceinline__ double2 inv_chol_warp(double2 a, int g, int t, double
 __host__ __device__ constexpr int mid_blocks(int nrb) { return MNBC * (MNBC + 1) / 2 + nrb * MNBC; }
 
 template <int NRB>
-struct MidWarp {
+struct alignas(16) MidWarp {
   double blk[mid_blocks(NRB)][64];
   double px[MKMAX], py[MKMAX], pz[MKMAX], pv[MKMAX];
   double G[NRB * (NRB + 1) / 2][64];
+  double Wb[2][64];                   // inverse diagonal factors, published one column ahead
   int sp[MKMAX];
+  int badflag;
 };
 
 template <int NRB>
@@ -200,40 +202,63 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       }
     pair_sync();
 
-    // ---- left-looking blocked Cholesky, right-hand-side rows included; blocks are overwritten by L ----
-    // Column kb: both warps form the diagonal block and its inverse factor (redundantly), each takes the block
-    // rows of its parity; one barrier per column makes the new L blocks visible to the partner.
+    // ---- left-looking blocked Cholesky with LOOK-AHEAD, right-hand-side rows included; blocks become L ----
+    // The chain "block row kb+1 of column kb -> diagonal block kb+1 -> its inverse factor" is the serial part:
+    // warp 0 of the pair (A) runs it one column ahead and publishes W in shared memory, while warp 1 (B) does every
+    // other block row of column kb (the right-hand sides included) and accumulates the Schur blocks.
     bool bad = false;
     double2 Gacc[NGB];
 #pragma unroll
     for (int q = 0; q < NGB; ++q) Gacc[q] = make_double2(0.0, 0.0);
+    if (h == 0) put(S.Wb[0], inv_chol_warp(frag(S.blk[lowidx(0, 0)]), g, t, GSM_PIVOT_RTOL * v.sill, bad));
+    pair_sync();
 #pragma unroll 1
     for (int kb = 0; kb < nbc; ++kb) {
-      double2 D = frag(S.blk[lowidx(kb, kb)]);
-#pragma unroll 1
-      for (int j = 0; j < kb; ++j) {
-        const double2 L = frag(S.blk[lowidx(kb, j)]);
-        upd(D, L, L);
-      }
-      const double2 W = inv_chol_warp(D, g, t, GSM_PIVOT_RTOL * v.sill, bad);
-#pragma unroll 1
-      for (int i = kb + 1; i < nbc + NRB; ++i) {
-        if ((i & 1) != h) continue;
-        const bool rhs = i >= nbc;
-        double* bi = rhs ? S.blk[rbase + (i - nbc) * MNBC + kb] : S.blk[lowidx(i, kb)];
-        double2 C = frag(bi);
-#pragma unroll 1
-        for (int j = 0; j < kb; ++j) {
-          const double2 X = frag(rhs ? S.blk[rbase + (i - nbc) * MNBC + j] : S.blk[lowidx(i, j)]);
-          const double2 Y = frag(S.blk[lowidx(kb, j)]);
-          upd(C, X, Y);
-        }
-        panel(C, W);
-        put(bi, C);
-      }
-      pair_sync();
-      // Schur blocks: G[r][q] -= L_Rr,kb L_Rq,kb' (warp 0 of the pair)
+      const double2 W = frag(S.Wb[kb & 1]);
       if (h == 0) {
+        if (kb + 1 < nbc) {
+          // row kb+1 of this column, then the next diagonal block and its inverse factor
+          double* bi = S.blk[lowidx(kb + 1, kb)];
+          double2 C = frag(bi);
+          double2 D = frag(S.blk[lowidx(kb + 1, kb + 1)]);
+#pragma unroll 1
+          for (int j = 0; j < kb; ++j) {
+            const double2 X = frag(S.blk[lowidx(kb + 1, j)]);
+            upd(C, X, frag(S.blk[lowidx(kb, j)]));
+            upd(D, X, X);
+          }
+          panel(C, W);
+          put(bi, C);
+          upd(D, C, C);
+          put(S.Wb[(kb + 1) & 1], inv_chol_warp(D, g, t, GSM_PIVOT_RTOL * v.sill, bad));
+        }
+      } else {
+#pragma unroll 1
+        for (int i = kb + 2; i < nbc + NRB; ++i) {
+          const bool rhs = i >= nbc;
+          double* bi = rhs ? S.blk[rbase + (i - nbc) * MNBC + kb] : S.blk[lowidx(i, kb)];
+          double2 C = frag(bi);
+#pragma unroll 1
+          for (int j = 0; j < kb; ++j) {
+            const double2 X = frag(rhs ? S.blk[rbase + (i - nbc) * MNBC + j] : S.blk[lowidx(i, j)]);
+            upd(C, X, frag(S.blk[lowidx(kb, j)]));
+          }
+          panel(C, W);
+          put(bi, C);
+        }
+        if (kb + 1 >= nbc) {
+          // (the first right-hand-side row is block row kb+1 of the last column: nobody looks ahead there)
+#pragma unroll 1
+          for (int i = kb + 1; i < min(kb + 2, nbc + NRB); ++i) {
+            double* bi = S.blk[rbase + (i - nbc) * MNBC + kb];
+            double2 C = frag(bi);
+#pragma unroll 1
+            for (int j = 0; j < kb; ++j) upd(C, frag(S.blk[rbase + (i - nbc) * MNBC + j]), frag(S.blk[lowidx(kb, j)]));
+            panel(C, W);
+            put(bi, C);
+          }
+        }
+        // Schur blocks: G[r][q] -= L_Rr,kb L_Rq,kb'
 #pragma unroll
         for (int r = 0; r < NRB; ++r)
 #pragma unroll
@@ -242,11 +267,17 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
             upd(Gacc[r * (r + 1) / 2 + q], X, Y);
           }
       }
+      pair_sync();
     }
-    if (h != 0) continue;                               // the epilogue belongs to warp 0 of the pair
+    if (h == 0) {
+      if (lane == 0) S.badflag = bad ? 1 : 0;
+    } else {
 #pragma unroll
-    for (int q = 0; q < NGB; ++q) put(S.G[q], Gacc[q]);
-    const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+      for (int q = 0; q < NGB; ++q) put(S.G[q], Gacc[q]);
+    }
+    pair_sync();
+    if (h != 0) continue;                               // the epilogue belongs to warp 0 of the pair
+    const unsigned anybad = S.badflag;
     __syncwarp();
 
     // ---- epilogue (one lane): -G[a][b], a >= b, stored as 8x8 blocks (0,0), (1,0), (1,1) ----
