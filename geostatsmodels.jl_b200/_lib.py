@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gsm_abi_version", "gsm_create", "gsm_destroy", "gsm_last_error", "gsm_get_timings", "gsm_get_summary", "gsm_synchronize",
     "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_set_samples_scaled", "gsm_knn", "gsm_local_krige",
     "gsm_global_krige_fit", "gsm_global_krige_status", "gsm_global_krige_predict", "gsm_global_krige_free",
-    "gsm_idw", "gsm_nn", "gsm_measure_fp64_peak",
+    "gsm_idw", "gsm_nn", "gsm_measure_fp64_peak", "gsm_set_option",
 ]
 
 
@@ -107,6 +107,7 @@ def load():
     lib.gsm_idw.argtypes = [vp, dbl, P(Targets), P(NeighborOpts), vp, vp]
     lib.gsm_nn.argtypes = [vp, P(Targets), vp]
     lib.gsm_measure_fp64_peak.argtypes = [vp, P(dbl), P(dbl)]
+    lib.gsm_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("gsm_last_error",):
@@ -243,6 +244,10 @@ class Context:
 
     def synchronize(self):
         self._check(self._lib.gsm_synchronize(self._h))
+
+    def set_option(self, key: str, value) -> None:
+        """developer options (gsm_set_option): local_impl, shr_smax, bin_occupancy"""
+        self._check(self._lib.gsm_set_option(self._h, str(key).encode(), str(value).encode()))
 
     def set_samples(self, coords, values, dim=None, n=None):
         """coords: (n, dim) float64 C-order numpy array, or a device pointer / torch tensor with dim, n."""

@@ -56,17 +56,7 @@ struct DeviceGuard {
   }
 };
 
-VarioDev make_vario(const gsm_variogram& v) {
-  VarioDev d;
-  d.kind = v.kind;
-  d.sill = v.sill;
-  d.nugget = v.nugget;
-  d.range = v.range;
-  d.inv_range = 1.0 / v.range;
-  d.cs = v.sill - v.nugget;
-  d.nadd = v.kind == GSM_VARIO_GAUSSIAN ? v.nugget + 1e-6 : v.nugget;
-  return d;
-}
+VarioDev make_vario(const gsm_variogram& v) { return gsm_make_vario(v); }
 
 int check_vario(gsm_ctx* ctx, const gsm_variogram* v) {
   if (!v || v->kind < GSM_VARIO_GAUSSIAN || v->kind > GSM_VARIO_EXPONENTIAL || !(v->range > 0.0) ||
@@ -331,6 +321,33 @@ int gsm_get_timings(const gsm_ctx* ctx, gsm_timings* out) {
   return GSM_OK;
 }
 
+int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value) {
+  if (!ctx || !key || !value) return GSM_ERR_INVALID;
+  const std::string k = key, v = value;
+  if (k == "local_impl") {
+    if (v == "auto") ctx->opt_local_impl = GSM_IMPL_AUTO;
+    else if (v == "shr") ctx->opt_local_impl = GSM_IMPL_SHR;
+    else if (v == "pipe") ctx->opt_local_impl = GSM_IMPL_PIPE;
+    else if (v == "simt") ctx->opt_local_impl = GSM_IMPL_SIMT;
+    else if (v == "patch") ctx->opt_local_impl = GSM_IMPL_PATCH;
+    else {
+      gsm_set_error(ctx, "gsm_set_option: local_impl must be auto | patch | shr | pipe | simt");
+      return GSM_ERR_INVALID;
+    }
+    return GSM_OK;
+  }
+  if (k == "shr_smax") {
+    ctx->opt_shr_smax = std::max(0, std::min(3, atoi(value)));
+    return GSM_OK;
+  }
+  if (k == "bin_occupancy") {
+    ctx->opt_bin_occupancy = atof(value);   // takes effect at the next gsm_set_samples
+    return GSM_OK;
+  }
+  gsm_set_error(ctx, "gsm_set_option: unknown key " + k);
+  return GSM_ERR_INVALID;
+}
+
 int gsm_synchronize(gsm_ctx* ctx) {
   if (!ctx) return GSM_ERR_INVALID;
   DeviceGuard g(ctx->device);
@@ -421,9 +438,27 @@ int gsm_set_samples_scaled(gsm_ctx* ctx, const double* coords, int32_t dim, int6
 
 // Shared driver of the neighbourhood-based entry points.
 //   mode 0: kNN only, 1: local Kriging, 2: local IDW
+static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const gsm_model* model, double exponent,
+                          const gsm_targets* targets, const gsm_neighbor_opts* opts, double* out_mean, double* out_var,
+                          uint8_t* out_status, int32_t* out_nbr, int32_t* out_n);
 static int run_local(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const gsm_model* model, double exponent,
                      const gsm_targets* targets, const gsm_neighbor_opts* opts, double* out_mean, double* out_var,
                      uint8_t* out_status, int32_t* out_nbr, int32_t* out_n) {
+  const int rc = run_local_body(ctx, mode, vario, model, exponent, targets, opts, out_mean, out_var, out_status, out_nbr,
+                                out_n);
+  if (rc != GSM_OK && ctx) {
+    // an early return may leave asynchronous downloads into caller memory in flight: drain both streams so no
+    // buffer (the caller's, or a pooled pinned one) is recycled under a running copy
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaGetLastError();
+  }
+  return rc;
+}
+static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, const gsm_model* model, double exponent,
+                          const gsm_targets* targets, const gsm_neighbor_opts* opts, double* out_mean, double* out_var,
+                          uint8_t* out_status, int32_t* out_nbr, int32_t* out_n) {
   if (!ctx) return GSM_ERR_INVALID;
   if (ctx->n <= 0) {
     gsm_set_error(ctx, "no samples: call gsm_set_samples first");

@@ -121,8 +121,8 @@ __global__ void sort_cells_kernel(int ncells, const int* __restrict__ cell_start
 }  // namespace
 
 // Average samples per cell the bins aim for.  Tuned on B200 (kNN kernel).
-static double target_occupancy(int dim) {
-  if (const char* e = getenv("GSM_BIN_OCCUPANCY")) return atof(e);   // developer switch (tuning)
+static double target_occupancy(const gsm_ctx* ctx, int dim) {
+  if (ctx->opt_bin_occupancy > 0.0) return ctx->opt_bin_occupancy;   // developer option "bin_occupancy" (tuning)
   return dim >= 3 ? 2.2 : 2.0;
 }
 
@@ -175,7 +175,7 @@ int gsm_build_bins(gsm_ctx* ctx) {
   if (live == 0) {
     h = 1.0;
   } else {
-    h = std::pow(target_occupancy(live) * vol / (double)n, 1.0 / live);
+    h = std::pow(target_occupancy(ctx, live) * vol / (double)n, 1.0 / live);
   }
   // cap the total number of cells (memory) by growing h if needed
   const double max_cells = 64.0 * 1024 * 1024;

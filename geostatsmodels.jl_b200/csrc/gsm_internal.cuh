@@ -44,9 +44,24 @@ void gsm_set_error(gsm_ctx* ctx, const std::string& msg);
 struct VarioDev {
   int kind;
   double sill, nugget, range, inv_range;
-  double cs;    // sill - nugget (partial sill)
+  double cs;    // partial sill: sill - nadd
   double nadd;  // nugget added for h > 0 (Gaussian: nugget + 1e-6)
 };
+
+// The ONE place where a variogram descriptor becomes device constants (include/gsm_b200.h lists the formulas).
+// GaussianVariogram replaces the nugget by n' = nugget + 1e-6 BEFORE forming the partial sill:
+// gamma(h) = (sill - n')(1 - exp(-3 t^2)) + (h > 0) n'  (oracle GAUSSIAN_NUGGET_EPS).
+inline VarioDev gsm_make_vario(const gsm_variogram& v) {
+  VarioDev d;
+  d.kind = v.kind;
+  d.sill = v.sill;
+  d.nugget = v.nugget;
+  d.range = v.range;
+  d.inv_range = 1.0 / v.range;
+  d.nadd = v.kind == GSM_VARIO_GAUSSIAN ? v.nugget + 1e-6 : v.nugget;
+  d.cs = v.sill - d.nadd;
+  return d;
+}
 
 struct TargetsDev {
   int kind;               // GSM_TARGETS_GRID / POINTS
@@ -85,8 +100,15 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+// gsm_set_option(ctx, "local_impl", ...): which local-Kriging kernel serves k <= 32 (default: dispatch by shape)
+enum { GSM_IMPL_AUTO = 0, GSM_IMPL_SHR = 1, GSM_IMPL_PIPE = 2, GSM_IMPL_SIMT = 3, GSM_IMPL_PATCH = 4 };
+
 struct gsm_ctx {
   int device = 0;
+  // developer options (gsm_set_option; never read from the environment)
+  int opt_local_impl = GSM_IMPL_AUTO;
+  int opt_shr_smax = 3;            // cap on the shared block columns of the shared-factor kernel
+  double opt_bin_occupancy = 0.0;  // samples per bin cell of the neighbour search (0: default)
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // D2H overlap
   std::string err;
@@ -151,9 +173,6 @@ int gsm_launch_nbr_to_rows(gsm_ctx* ctx, const int* d_pos, long long total, int*
 int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k,
                            int minneighbors, const int* d_pos, const int* d_cnt, double* d_mean,
                            double* d_var, unsigned char* d_status);
-int gsm_launch_local_krige_dmma(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
-                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
-                                double* d_mean, double* d_var, unsigned char* d_status);
 int gsm_launch_local_krige_pipe(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                 const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                 double* d_mean, double* d_var, unsigned char* d_status);
@@ -161,9 +180,6 @@ int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& 
                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                double* d_mean, double* d_var, unsigned char* d_status);
 int gsm_launch_local_krige_mid(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
-                               const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
-                               double* d_mean, double* d_var, unsigned char* d_status);
-int gsm_launch_local_krige_big(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                double* d_mean, double* d_var, unsigned char* d_status);
 int gsm_launch_idw_global(gsm_ctx* ctx, double exponent, const TargetsDev& tg, double* d_mean);

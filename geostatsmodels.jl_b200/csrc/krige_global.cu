@@ -209,143 +209,6 @@ struct GlobalDev {
   double hw[GSM_MAX_DRIFT];
 };
 
-__global__ void __launch_bounds__(PTHREADS) global_predict_kernel(GlobalDev gd, VarioDev v, ModelDev m, TargetsDev tg,
-                                                                 double* __restrict__ out_mean,
-                                                                 double* __restrict__ out_var) {
-  __shared__ __align__(16) double As[PK * PLDA];
-  __shared__ __align__(16) double Bs[PT * PLDB];
-  __shared__ double tx[PT], ty[PT], tz[PT];
-  __shared__ double uu[PT];
-  __shared__ double dots[(1 + GSM_MAX_DRIFT) * PT];
-  __shared__ double red[4][PT];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
-  const long long t0 = blockIdx.x * (long long)PT;
-  const int ncon = gd.ncon, np = gd.np, n = gd.n;
-  if (tid < PT) {
-    double x = 0, y = 0, z = 0;
-    if (t0 + tid < tg.count) gsm_target_coords(tg, tg.first + t0 + tid, x, y, z);
-    tx[tid] = x;
-    ty[tid] = y;
-    tz[tid] = z;
-    uu[tid] = 0.0;
-  }
-  for (int e = tid; e < (1 + GSM_MAX_DRIFT) * PT; e += PTHREADS) dots[e] = 0.0;
-  __syncthreads();
-  // the thread's fixed (k, target) slots in the r tile: 16 x 64 = 1024 entries, 4 per thread
-  const int rk = tid & 15;          // k within the tile
-  const int rn0 = tid >> 4;         // target 0..15, +16, +32, +48
-  double dacc[4][1 + GSM_MAX_DRIFT];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    for (int c = 0; c <= GSM_MAX_DRIFT; ++c) dacc[q][c] = 0.0;
-
-  const int nib = np / PM;
-  for (int ib = 0; ib < nib; ++ib) {
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int kend = (ib + 1) * PM;   // Linv is lower triangular: columns beyond the row block are zero
-    const bool last = (ib == nib - 1);
-    for (int k0 = 0; k0 < kend; k0 += PK) {
-      // A tile: Linv[ib*PM + m][k0 + k]
-      for (int e = tid; e < PK * PM; e += PTHREADS) {
-        int mm = e % PM, k = e / PM;
-        As[k * PLDA + mm] = gd.Linv[(size_t)(k0 + k) * np + ib * PM + mm];
-      }
-      // r tile: covariance between sample k0+rk and the tile's targets
-      {
-        const int s = k0 + rk;
-        const bool live = s < n;
-        const double sx = live ? gd.px[s] : 0.0, sy = live ? gd.py[s] : 0.0, sz = live ? gd.pz[s] : 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int nn = rn0 + 16 * q;
-          double r = 0.0;
-          if (live) {
-            const double dx = sx - tx[nn], dy = sy - ty[nn], dz = sz - tz[nn];
-            r = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
-          }
-          Bs[nn * PLDB + rk] = r;
-          if (last && live) {
-            dacc[q][0] = fma(gd.D[s], r, dacc[q][0]);
-            for (int c = 1; c <= ncon; ++c) dacc[q][c] = fma(gd.D[(size_t)c * np + s], r, dacc[q][c]);
-          }
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < PK; kk += 4) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = As[(kk + t) * PLDA + wm + i * 8 + g];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = Bs[(wn + j * 8 + g) * PLDB + kk + t];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-      }
-      __syncthreads();
-    }
-    // column sums of squares over this row block
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        double p = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) p = fma(acc[i][j][s], acc[i][j][s], p);
-        p += __shfl_xor_sync(0xffffffffu, p, 4);
-        p += __shfl_xor_sync(0xffffffffu, p, 8);
-        p += __shfl_xor_sync(0xffffffffu, p, 16);
-        if (g == 0) red[warp & 3][wn + j * 8 + 2 * t + s] = p;
-      }
-    __syncthreads();
-    if (tid < PT) uu[tid] += (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-    __syncthreads();
-  }
-  // reduce the per-thread dot products over the 16 k-lanes of each target
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    for (int c = 0; c <= ncon; ++c) {
-      double p = dacc[q][c];
-      p += __shfl_xor_sync(0xffffffffu, p, 1);
-      p += __shfl_xor_sync(0xffffffffu, p, 2);
-      p += __shfl_xor_sync(0xffffffffu, p, 4);
-      p += __shfl_xor_sync(0xffffffffu, p, 8);
-      if (rk == 0) dots[c * PT + rn0 + 16 * q] = p;
-    }
-  __syncthreads();
-  if (tid < PT && t0 + tid < tg.count) {
-    const double c0 = v.sill;
-    double mean = dots[tid], var = c0 - uu[tid];
-    if (m.kind == GSM_KRIG_SIMPLE) {
-      mean += m.mean;
-    } else {
-      double gq[GSM_MAX_DRIFT], nu[GSM_MAX_DRIFT];
-      for (int c = 0; c < ncon; ++c) {
-        const double f0 = (m.kind == GSM_KRIG_ORDINARY) ? 1.0 : gsm_drift(m, c, tx[tid], ty[tid], tz[tid]);
-        gq[c] = dots[(1 + c) * PT + tid] - f0;
-      }
-      for (int c = 0; c < ncon; ++c) {
-        double s = 0.0;
-        for (int d = 0; d < ncon; ++d) s = fma(gd.Ginv[c * ncon + d], gq[d], s);
-        nu[c] = s;
-      }
-      for (int c = 0; c < ncon; ++c) {
-        mean = fma(-gd.hw[c], nu[c], mean);
-        var = fma(gq[c], nu[c], var);
-      }
-    }
-    out_mean[t0 + tid] = mean;
-    if (out_var) out_var[t0 + tid] = var + 1e-10;
-  }
-}
-
 // ---- batched prediction (default): covariance tile once, then a triangular DMMA GEMM with a norm epilogue ----
 // For a batch of Mb targets:
 //   1. global_r_kernel     R[k][n] = cov(sample k, target n), k-major (np x Mb), written once; and the inner
@@ -354,8 +217,8 @@ __global__ void __launch_bounds__(PTHREADS) global_predict_kernel(GlobalDev gd, 
 //                          (3-stage cp.async pipeline, Linv lower triangular so K stops at the block's last row)
 //                          and adds the column sums of squares to uu[n] = |Linv c0(n)|^2 = c0' C^-1 c0.
 //   3. global_finish       mean, variance and the drift correction per target.
-// The first version (global_predict_kernel above) rebuilt the covariance tile for every row block (16x redundant
-// at N = 4000) and had no load / compute overlap; it is kept as GSM_GLOBAL_IMPL=v1.
+// (The first version rebuilt the covariance tile for every row block, 16x redundant at N = 4000, with no load /
+// compute overlap: 969 ms against 582 ms at C2; removed in round 2.)
 constexpr int QK = 16;            // k step
 constexpr int QLDA = PM + 4;      // As[k][m]: stride = 4 mod 16 doubles -> the (t, g) fragment loads are conflict-free
 constexpr int QLDB = PT + 4;      // Bs[k][n]
@@ -634,14 +497,7 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
   double* pz = py + np;
   cudaMemsetAsync(b.info.p, 0, sizeof(int), st);
 
-  VarioDev vd;
-  vd.kind = vario->kind;
-  vd.sill = vario->sill;
-  vd.nugget = vario->nugget;
-  vd.range = vario->range;
-  vd.inv_range = 1.0 / vario->range;
-  vd.cs = vario->sill - vario->nugget;
-  vd.nadd = vario->kind == GSM_VARIO_GAUSSIAN ? vario->nugget + 1e-6 : vario->nugget;
+  const VarioDev vd = gsm_make_vario(*vario);
   ModelDev md{};
   md.kind = model->kind;
   md.mean = model->mean;
@@ -862,27 +718,14 @@ int gsm_global_krige_predict(gsm_fit* f, const gsm_targets* t, double* out_mean,
     gd.ncon = f->ncon;
     for (int a = 0; a < f->ncon * f->ncon; ++a) gd.Ginv[a] = f->S[a];
     for (int a = 0; a < f->ncon; ++a) gd.hw[a] = f->h[a];
-    VarioDev vd;
-    vd.kind = f->vario.kind;
-    vd.sill = f->vario.sill;
-    vd.nugget = f->vario.nugget;
-    vd.range = f->vario.range;
-    vd.inv_range = 1.0 / f->vario.range;
-    vd.cs = f->vario.sill - f->vario.nugget;
-    vd.nadd = f->vario.kind == GSM_VARIO_GAUSSIAN ? f->vario.nugget + 1e-6 : f->vario.nugget;
+    const VarioDev vd = gsm_make_vario(f->vario);
     ModelDev md{};
     md.kind = f->model.kind;
     md.mean = f->model.mean;
     md.ndrift = f->model.kind == GSM_KRIG_UNIVERSAL ? f->model.ndrift : 0;
     for (int a = 0; a < md.ndrift; ++a)
       for (int d = 0; d < 3; ++d) md.exps[a][d] = f->model.exps[a][d];
-    const char* impl_env = getenv("GSM_GLOBAL_IMPL");
-    if (impl_env && std::string(impl_env) == "v1") {
-      const unsigned blocks = (unsigned)((count + PT - 1) / PT);
-      global_predict_kernel<<<blocks, PTHREADS, 0, st>>>(gd, vd, md, td, dmean, dvar);
-      ctx->tim.launches++;
-      GSM_CUDA(ctx, cudaGetLastError());
-    } else {
+    {
       // batches of mb targets: the covariance tile R (np x mb, k-major) stays around 256 MB
       long long mb = (256LL << 20) / ((long long)np * 8) / PT * PT;
       mb = std::max<long long>(PT, std::min<long long>(mb, 8192));

@@ -71,7 +71,7 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   __syncwarp();
 
   // ---- assemble C (covariance form), half the pairs per lane, mirrored through shared memory --
-  sm.C[lane * LK_LD + lane] = live ? v.sill : 1.0;
+  sm.C[lane * LK_LD + lane] = v.sill;   // (padding rows too: the pivot test is relative to the sill)
 #pragma unroll 4
   for (int s = 1; s <= 16; ++s) {
     const int c = (lane + s) & 31;
@@ -170,9 +170,10 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
       for (int q = 0; q <= p; ++q) G[p * NCON + q] = gsm_warp_sum(rhs[2 + p] * rhs[2 + q]);
     }
     // Cholesky of G (every lane redundantly, registers), solve G nu = g
-#pragma unroll
     double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
+#pragma unroll
     for (int p0_ = 0; p0_ < NCON; ++p0_) gd0[p0_] = G[p0_ * NCON + p0_];
+#pragma unroll
     for (int j = 0; j < NCON; ++j) {
       double d = G[j * NCON + j];
       if (!(d > GSM_SCHUR_RTOL * gd0[j])) {
@@ -262,23 +263,13 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool nonconst = false;
   for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
   const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
-  if (k > 32) {
-    // 32 < k <= 64: warp-per-system DMMA kernel with the matrix in shared memory (krige_local_mid.cu);
-    // GSM_LOCAL_IMPL=big selects the first, CTA-per-system SIMT version
-    const char* e = getenv("GSM_LOCAL_IMPL");
-    if (!(e && std::string(e) == "big")) {
-      int rc = gsm_launch_local_krige_mid(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
-                                          d_status);
-      if (rc != GSM_ERR_UNSUPPORTED) return rc;
-    }
-    return gsm_launch_local_krige_big(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
+  if (k > 32)   // 32 < k <= 64: the matrix lives in shared memory (krige_local_mid.cu)
+    return gsm_launch_local_krige_mid(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                       d_status);
-  }
   // Default: the shared-factor kernel for grid targets with more than one block column (k > 8: neighbouring
   // targets share most neighbours, krige_local_shr.cuh), the pipelined kernel otherwise (k <= 8, or explicit
-  // points whose order says nothing about their proximity).  GSM_LOCAL_IMPL = shr | pipe | dmma | v1 overrides
-  // (A/B profiling; read per call so one process can compare them).
-  const char* impl_env = getenv("GSM_LOCAL_IMPL");
+  // points whose order says nothing about their proximity).  gsm_set_option(ctx, "local_impl", ...) overrides
+  // (A/B profiling and the per-kernel parity tests); no environment variable is read on a product call.
   bool patches = tg.kind == GSM_TARGETS_GRID && tg.dim >= 2 && tg.dims[1] > 1;
   if (patches) {
     // Sharing pays when the neighbourhood is wide compared with a patch: radius of the k nearest samples in units
@@ -296,19 +287,15 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
       if (rk < (d == 3 ? 3.0 : 5.0)) patches = false;
     }
   }
-  const std::string impl = impl_env ? impl_env : ((k > 8 && patches) ? "shr" : "pipe");
-  if (impl == "shr") {
+  int impl = ctx->opt_local_impl;
+  if (impl == GSM_IMPL_AUTO) impl = (k > 8 && patches) ? GSM_IMPL_SHR : GSM_IMPL_PIPE;
+  if (impl == GSM_IMPL_SHR) {
     int rc = gsm_launch_local_krige_shr(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                         d_status);
     if (rc != GSM_ERR_UNSUPPORTED) return rc;
   }
-  if (impl == "pipe" || impl == "shr") {
+  if (impl == GSM_IMPL_PIPE || impl == GSM_IMPL_SHR) {
     int rc = gsm_launch_local_krige_pipe(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
-                                         d_status);
-    if (rc != GSM_ERR_UNSUPPORTED) return rc;
-  }
-  if (impl == "dmma") {
-    int rc = gsm_launch_local_krige_dmma(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                          d_status);
     if (rc != GSM_ERR_UNSUPPORTED) return rc;
   }

@@ -164,7 +164,7 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           const int col = c0 + s;
-          double val = (row == col) ? 1.0 : 0.0;
+          double val = (row == col) ? v.sill : 0.0;   // padding: sill * identity
           if (row < n && col < n) {
             val = v.sill;
             if (row != col) {

@@ -257,9 +257,10 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
 #pragma unroll
             for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, tx, ty, tz);
           }
-#pragma unroll
           double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
+#pragma unroll
           for (int p0_ = 0; p0_ < NCON; ++p0_) gd0[p0_] = Gs[p0_ * NCON + p0_];
+#pragma unroll
           for (int j = 0; j < NCON; ++j) {
             double d = Gs[j * NCON + j];
             if (!(d > GSM_SCHUR_RTOL * gd0[j])) {
@@ -482,7 +483,7 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
         return make_double2(S.PC[rbase[I] + icol[J].x], S.PC[rbase[I] + icol[J].y]);
       }
       const int row = 8 * I + g, col = 8 * J + 2 * t;
-      double c0 = (row == col) ? 1.0 : 0.0, c1 = (row == col + 1) ? 1.0 : 0.0;
+      double c0 = (row == col) ? v.sill : 0.0, c1 = (row == col + 1) ? v.sill : 0.0;   // padding: sill * identity
       if (pooled) {
         const int ir = irow[I], ix = icol[J].x, iy = icol[J].y;
         if (ir >= 0 && ix >= 0) c0 = S.PC[ir * PLD + ix];
@@ -498,8 +499,8 @@ local_krige_pipe_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k,
         const double e0 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
         dx = xr - xc.y, dy = yr - yc.y, dz = zr - zc.y;
         const double e1 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
-        c0 = (row == col) ? (rowlive ? v.sill : 1.0) : ((rowlive && col < n) ? e0 : 0.0);
-        c1 = (row == col + 1) ? (rowlive ? v.sill : 1.0) : ((rowlive && col + 1 < n) ? e1 : 0.0);
+        c0 = (row == col) ? v.sill : ((rowlive && col < n) ? e0 : 0.0);
+        c1 = (row == col + 1) ? v.sill : ((rowlive && col + 1 < n) ? e1 : 0.0);
       }
       return make_double2(c0, c1);
     };

@@ -199,7 +199,7 @@ int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& 
   };
   mark();
   int smax = nbc - 1;
-  if (const char* e = getenv("GSM_SHR_SMAX")) smax = std::min(smax, atoi(e));   // developer switch: cap the sharing
+  smax = std::min(smax, ctx->opt_shr_smax);   // developer option "shr_smax": cap the sharing
   job_index_kernel<<<ixblocks, IX_WARPS * 32, 0, ctx->stream>>>(tg, gm, k, 8 * nbc, smax, minneighbors, d_pos, d_cnt, jobs);
   ctx->tim.launches++;
   mark();

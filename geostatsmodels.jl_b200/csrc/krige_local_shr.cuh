@@ -166,7 +166,7 @@ __device__ __noinline__ double2 gath_cold(const double* __restrict__ PC, bool po
                                           int col, int n, const double* __restrict__ px,
                                           const double* __restrict__ py, const double* __restrict__ pz,
                                           const VarioDev* vp) {
-  double c0 = (row == col) ? 1.0 : 0.0, c1 = (row == col + 1) ? 1.0 : 0.0;
+  double c0 = (row == col) ? vp->sill : 0.0, c1 = (row == col + 1) ? vp->sill : 0.0;   // padding: sill * identity
   if (pooled) {
     if (ir >= 0 && ix >= 0) c0 = PC[ir * PLD + ix];
     if (ir >= 0 && iy >= 0) c1 = PC[ir * PLD + iy];
@@ -178,8 +178,8 @@ __device__ __noinline__ double2 gath_cold(const double* __restrict__ PC, bool po
     const double e0 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
     dx = xr - px[col + 1], dy = yr - py[col + 1], dz = DIM3 ? zr - pz[col + 1] : 0.0;
     const double e1 = cov_fast(cf, DIM3 ? fma(dz, dz, fma(dy, dy, dx * dx)) : fma(dy, dy, dx * dx));
-    c0 = (row == col) ? (rowlive ? vp->sill : 1.0) : ((rowlive && col < n) ? e0 : 0.0);
-    c1 = (row == col + 1) ? (rowlive ? vp->sill : 1.0) : ((rowlive && col + 1 < n) ? e1 : 0.0);
+    c0 = (row == col) ? vp->sill : ((rowlive && col < n) ? e0 : 0.0);
+    c1 = (row == col + 1) ? vp->sill : ((rowlive && col + 1 < n) ? e1 : 0.0);
   }
   return make_double2(c0, c1);
 }
@@ -348,9 +348,10 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
 #pragma unroll
             for (int p = 0; p < NCON; ++p) gq[p] -= gsm_drift(m, p, tx, ty, tz);
           }
-#pragma unroll
           double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
+#pragma unroll
           for (int p0_ = 0; p0_ < NCON; ++p0_) gd0[p0_] = Gs[p0_ * NCON + p0_];
+#pragma unroll
           for (int j2 = 0; j2 < NCON; ++j2) {
             double d = Gs[j2 * NCON + j2];
             if (!(d > GSM_SCHUR_RTOL * gd0[j2])) {

@@ -54,7 +54,7 @@ enum {
 
 /* GeoStatsFunctions variogram, isotropic, Euclidean metric ball (call sites krig.jl:125,347,297).
  * gamma(h), t = h/range:
- *   GAUSSIAN     (sill-nugget)(1-exp(-3t^2)) + (h>0)(nugget+1e-6)
+ *   GAUSSIAN     (sill-n')(1-exp(-3t^2)) + (h>0) n',  n' = nugget + 1e-6 (the floor replaces the nugget everywhere)
  *   SPHERICAL    (sill-nugget)(1.5t-0.5t^3) for h<range, (sill-nugget) otherwise, + (h>0) nugget
  *   EXPONENTIAL  (sill-nugget)(1-exp(-3t)) + (h>0) nugget
  * The system is assembled in covariance form sill - gamma(h) (krig.jl:165-179, 364-378). */
@@ -139,6 +139,10 @@ GSM_API const char* gsm_last_error(const gsm_ctx* ctx);
 GSM_API int gsm_get_timings(const gsm_ctx* ctx, gsm_timings* out);
 GSM_API int gsm_get_summary(const gsm_ctx* ctx, gsm_summary* out);
 GSM_API int gsm_synchronize(gsm_ctx* ctx);
+/* Developer options (A/B profiling and per-kernel parity tests; the defaults are the product, and the library
+ * reads no environment variable): "local_impl" = auto | patch | shr | pipe | simt (which local-Kriging kernel serves
+ * maxneighbors <= 32), "shr_smax" = 0..3, "bin_occupancy" = samples per search cell (next gsm_set_samples). */
+GSM_API int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value);
 
 /* Pinned host buffers so outputs DMA straight into caller-owned memory (Julia: unsafe_wrap). */
 GSM_API int gsm_host_alloc(void** out, int64_t bytes);

@@ -34,7 +34,7 @@ typedef struct { int kind; double mean; int ndrift; int exps[MAXCON][3]; } omode
 /* ---------------------------------------------------------------- variogram (gsm_oracle.py twin) */
 static double gamma_h(const ovario* v, double h) {
   double s = v->sill, n = v->nugget, r = v->range, t = h / r, g;
-  if (v->kind == 0) return (s - n) * (1.0 - exp(-3.0 * (t * t))) + (h > 0 ? (n + 1e-6) : 0.0);
+  if (v->kind == 0) { n = n + 1e-6; return (s - n) * (1.0 - exp(-3.0 * (t * t))) + (h > 0 ? n : 0.0); }  /* n' everywhere */
   if (v->kind == 1) {
     g = (h < r) ? (s - n) * (1.5 * t - 0.5 * (t * t * t)) : (s - n);
     return g + (h > 0 ? n : 0.0);

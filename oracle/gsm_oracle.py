@@ -46,6 +46,10 @@ _KIND_NAMES = {"gaussian": GAUSSIAN, "spherical": SPHERICAL, "exponential": EXPO
 
 # GaussianVariogram adds a small epsilon to the nugget "for numerical stability" (restated from
 # GeoStatsFunctions; unpinned by any reference test).  One switch so it can be corrected in one place.
+# The modified nugget n' = nugget + eps replaces the nugget in BOTH terms:
+#   gamma(h) = (sill - n') (1 - exp(-3 (h/r)^2)) + (h > 0) n'
+# so gamma still saturates at the total sill.  (Round 1 used (sill - nugget) in the first term, which overshoots
+# the sill by eps; corrected in round 2 in the oracle, its C twin and gsm_make_vario together.)
 GAUSSIAN_NUGGET_EPS = 1e-6
 
 
@@ -67,7 +71,8 @@ def variogram(v: Variogram, h):
     s, n, r = v.sill, v.nugget, v.range
     if v.kind == GAUSSIAN:
         t = h / r
-        return (s - n) * (1.0 - np.exp(-3.0 * (t * t))) + (h > 0) * (n + GAUSSIAN_NUGGET_EPS)
+        n = n + GAUSSIAN_NUGGET_EPS
+        return (s - n) * (1.0 - np.exp(-3.0 * (t * t))) + (h > 0) * n
     if v.kind == SPHERICAL:
         t = h / r
         poly = (s - n) * (1.5 * t - 0.5 * (t * t * t))

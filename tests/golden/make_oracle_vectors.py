@@ -40,7 +40,16 @@ def build(case):
         mu, var, st = o.fitpredict(model, X, z, grid, prob=prob, maxneighbors=k)
     else:
         mu, var, st = o.fitpredict(model, X, z, grid, prob=prob, neighbors=False)
-    return {"X": X, "z": z, "mean": mu, "var": var if var is not None else np.zeros(0), "status": st}
+    out = {"X": X, "z": z, "mean": mu, "var": var if var is not None else np.zeros(0), "status": st}
+    if k and prob:
+        # the exact (binary128, oracle/gsm_oracle_q.c) solution of the same equations on the same neighbour lists:
+        # the referee for the ill-conditioned UniversalKriging cases, where float64 Bunch-Kaufman on raw monomials
+        # is itself several digits away from the solution of its own system
+        import gsm_oracle_c as oc
+        _, _, _, mu_q, var_q, ok_q = oc.fitpredict_exact(model, X, z, grid, maxneighbors=k, nthreads=4)
+        assert ok_q.all()
+        out["mean_exact"], out["var_exact"] = mu_q, var_q
+    return out
 
 
 if __name__ == "__main__":
