@@ -496,11 +496,16 @@ def test_sill_spans_orders_of_magnitude(gsm, oracle, sill, k, dims):
     for kind in ("ok", "sk", "uk"):
         om = _oracle_model(o, kind, vario, 2, mean=float(z.mean()), deg=1)
         gm = _gsm_model(gsm, kind, vario, 2, mean=float(z.mean()), deg=1)
-        mu, var, st, _, _ = oc.fitpredict(om, X, z, o.Grid((0.0, 0.0), (1.0, 1.0), dims), prob=True, maxneighbors=k, nthreads=4)
+        og = o.Grid((0.0, 0.0), (1.0, 1.0), dims)
+        if kind == "uk":   # referee: the exact (binary128) solution (the float64 oracle loses digits on raw monomials)
+            _, _, st, mu, var, okq = oc.fitpredict_exact(om, X, z, og, maxneighbors=k, nthreads=4)
+            assert okq.all()
+        else:
+            mu, var, st, _, _ = oc.fitpredict(om, X, z, og, prob=True, maxneighbors=k, nthreads=4)
         got = gsm.fitpredict(gm, gsm.georef({"z": z}, gsm.PointSet(X)), gsm.CartesianGrid(*dims), maxneighbors=k, prob=True).z
         assert (st == 0).all() and np.isfinite(np.asarray(got.mu)).all()
-        assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL * 1e6)
-        assert np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL * max(sill, 1e-10))
+        assert np.allclose(got.mu, mu, rtol=RTOL, atol=ATOL * 1e6), (kind, np.abs(got.mu - mu).max())
+        assert np.allclose(got.sigma, var, rtol=RTOL, atol=ATOL * max(sill, 1e-10)), (kind, np.abs(got.sigma - var).max())
 
 
 # ------------------------------------------------------------ shared-factor kernel, steady state
@@ -732,16 +737,18 @@ def test_c2_class_gaussian_local_against_exact_arithmetic(gsm, oracle):
             assert np.allclose(mu1[idx], r["mu_q"], rtol=1e-9, atol=1e-11), rep     # kappa ~ 1e4 / nugget
             assert np.allclose(var1[idx], r["var_q"], rtol=1e-9, atol=1e-11), rep
         else:
-            # kappa ~ 1e6 .. 1e9 (the 1e-6 floor): no float64 solver holds 1e-10 here; the GPU must be no worse than
-            # the float64 reference algorithm and must not flag systems the reference solves
+            # kappa ~ 1e6 .. 1e9 (only the 1e-6 floor regularises): no float64 solver holds 1e-10 here;
+            # the bar is the conditioning bound: forward error <= 100 * pivot ratio * 2^-53, on both sides, and the GPU
+            # must not flag systems the reference solves
             assert gpu_sing.sum() <= (r["st64"] == 2).sum(), rep
+            bound = 100.0 * r["pivot_ratio"].max() * 2.0 ** -53
             e_gpu = np.abs(np.where(gpu_sing, r["mu_q"], mu1[idx]) - r["mu_q"]).max()
             e_o = np.abs(r["mu64"] - r["mu_q"]).max()
-            assert e_gpu <= max(10 * e_o, 1e-9), rep
+            assert e_gpu <= bound and e_o <= bound, rep
 
 
 def test_randomised_parity_sweep(gsm, oracle):
-    """200 random neighbourhood cases (model, variogram, dimension, k up to 64, grid shape, slab, radius,
+    """120 random neighbourhood cases (model, variogram, dimension, k up to 64, grid shape, slab, radius,
     minneighbors, coincident samples) against the C oracle: tools/fuzz_parity.py."""
     import importlib.util, os
     spec = importlib.util.spec_from_file_location(
@@ -749,7 +756,7 @@ def test_randomised_parity_sweep(gsm, oracle):
     fz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fz)
     bad = []
-    for seed in range(5000, 5200):
+    for seed in range(5000, 5120):
         ok, desc = fz.one(seed)
         if not ok:
             bad.append(desc)

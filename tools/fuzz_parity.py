@@ -68,8 +68,13 @@ def one(seed):
     fun = cls(sill=vario.sill, range=vario.range, nugget=vario.nugget)
     gm = {"sk": lambda: gsm.SimpleKriging(fun, float(z.mean())), "ok": lambda: gsm.OrdinaryKriging(fun),
           "uk": lambda: gsm.UniversalKriging(fun, deg, dim)}[kind]()
-    # two referees on the same neighbour lists: the float64 reference algorithm and its binary128 evaluation
-    mu, var, st, mu_q, var_q, ok_q = oc.fitpredict_exact(om, X, z, og, neighborhood=nbh, count=count, nthreads=8, **kw)
+    # two referees on the same neighbour lists: the float64 reference algorithm and, for the ill-conditioned families
+    # (UK with raw monomials, coincident samples, Gaussian), its binary128 evaluation
+    if kind == "uk" or dups or vk == 0:
+        mu, var, st, mu_q, var_q, ok_q = oc.fitpredict_exact(om, X, z, og, neighborhood=nbh, count=count, nthreads=8, **kw)
+    else:
+        mu, var, st, _, _ = oc.fitpredict(om, X, z, og, prob=True, neighborhood=nbh, count=count, nthreads=8, **kw)
+        mu_q, var_q, ok_q = mu, var, st == 0
     try:
         got = gsm.fitpredict(gm, tab, grid, prob=True, neighborhood=nbh, count=-1 if count is None else count, **kw).z
     except ValueError as ex:   # non-positive variance: the oracle must see one too
@@ -91,11 +96,13 @@ def one(seed):
     vs = max(1.0, sill)
     def fine(g, ref, exact, scale):
         near_ref = np.abs(g - ref) <= tol * scale + tol * np.abs(ref)
-        near_exact = np.abs(g - exact) <= np.maximum(np.abs(ref - exact), tol * scale + tol * np.abs(exact))
-        return near_ref | near_exact
-    okm = fine(gmu[both], mu[both], mu_q[both], zs)
-    okv = fine(gvar[both], var[both], var_q[both], vs)
-    ok = ok and bool(okm.all() and okv.all())
+        if near_ref.all():
+            return True
+        # the targets that miss the float64 reference: no farther from the exact solution than the float64
+        # reference algorithm gets anywhere in this case (its own rounding on this family of systems)
+        worst_ref = float(np.abs(ref - exact).max())
+        return bool((np.abs(g - exact)[~near_ref] <= max(worst_ref, tol * scale)).all())
+    ok = ok and fine(gmu[both], mu[both], mu_q[both], zs) and fine(gvar[both], var[both], var_q[both], vs)
     if not ok and both.any():
         desc += " maxerr vs f64 mu %.2e var %.2e, vs exact mu %.2e var %.2e (f64 oracle vs exact %.2e %.2e) flagged o/g %d/%d" % (
             np.abs(gmu[both] - mu[both]).max(), np.abs(gvar[both] - var[both]).max(), np.abs(gmu[both] - mu_q[both]).max(),
