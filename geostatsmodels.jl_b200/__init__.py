@@ -6,5 +6,5 @@ The directory name carries a dot, so it is imported under the alias ``gsm_b200``
 from . import _lib
 from .api import *  # noqa: F401,F403
 from .api import monomial_exponents  # noqa: F401
-from ._lib import Context, GsmError, PinnedArray  # noqa: F401
+from ._lib import Context, GsmError, MultiContext, PinnedArray  # noqa: F401
 from . import distributed  # noqa: F401,E402

@@ -25,6 +25,9 @@ EXPORTED_SYMBOLS = [
     "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_set_samples_scaled", "gsm_knn", "gsm_local_krige",
     "gsm_global_krige_fit", "gsm_global_krige_status", "gsm_global_krige_predict", "gsm_global_krige_free",
     "gsm_idw", "gsm_nn", "gsm_measure_fp64_peak", "gsm_set_option",
+    "gsm_multi_create", "gsm_multi_destroy", "gsm_multi_last_error", "gsm_multi_device_count", "gsm_multi_context",
+    "gsm_multi_get_timings", "gsm_multi_get_summary", "gsm_multi_set_samples", "gsm_multi_set_samples_scaled",
+    "gsm_multi_slab", "gsm_multi_local_krige", "gsm_multi_idw", "gsm_multi_global_krige",
 ]
 
 
@@ -56,6 +59,14 @@ class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("bin_ms", C.c_double), ("knn_ms", C.c_double),
                 ("solve_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
                 ("launches", C.c_int64), ("index_ms", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class MultiTimings(C.Structure):
+    _fields_ = [("upload_ms", C.c_double), ("bcast_ms", C.c_double), ("bins_ms", C.c_double),
+                ("predict_ms", C.c_double), ("wall_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -108,9 +119,24 @@ def load():
     lib.gsm_nn.argtypes = [vp, P(Targets), vp]
     lib.gsm_measure_fp64_peak.argtypes = [vp, P(dbl), P(dbl)]
     lib.gsm_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
+    lib.gsm_multi_create.argtypes = [P(i32), i32, P(vp)]
+    lib.gsm_multi_destroy.argtypes = [vp]
+    lib.gsm_multi_last_error.argtypes = [vp]
+    lib.gsm_multi_last_error.restype = C.c_char_p
+    lib.gsm_multi_device_count.argtypes = [vp]
+    lib.gsm_multi_context.argtypes = [vp, i32]
+    lib.gsm_multi_context.restype = vp
+    lib.gsm_multi_get_timings.argtypes = [vp, P(MultiTimings)]
+    lib.gsm_multi_get_summary.argtypes = [vp, P(Summary)]
+    lib.gsm_multi_set_samples.argtypes = [vp, vp, i32, i64, vp]
+    lib.gsm_multi_set_samples_scaled.argtypes = [vp, vp, i32, i64, vp, C.c_double, P(C.c_double), P(C.c_int64)]
+    lib.gsm_multi_slab.argtypes = [vp, P(Targets), i32, P(i64), P(i64)]
+    lib.gsm_multi_local_krige.argtypes = [vp, P(Variogram), P(Model), P(Targets), P(NeighborOpts), vp, vp, vp]
+    lib.gsm_multi_idw.argtypes = [vp, dbl, P(Targets), P(NeighborOpts), vp, vp]
+    lib.gsm_multi_global_krige.argtypes = [vp, P(Variogram), P(Model), P(Targets), vp, vp, P(i32)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("gsm_last_error",):
+        if name not in ("gsm_last_error", "gsm_multi_last_error", "gsm_multi_context"):
             fn.restype = C.c_int
     _LIB = lib
     return lib
@@ -368,6 +394,121 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._check(self._lib.gsm_measure_fp64_peak(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class MultiContext:
+    """All GPUs of a box behind ONE handle (gsm_multi_*): samples uploaded once and replicated by an NCCL broadcast,
+    the target range split into contiguous slabs, one host thread per device, outputs written straight into the
+    caller's host arrays.  Mirrors the Context methods fitpredict needs."""
+
+    def __init__(self, devices):
+        self._lib = load()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self._lib.gsm_multi_create(devs, len(devices), C.byref(h))
+        if rc != GSM_OK:
+            raise GsmError(rc, (self._lib.gsm_multi_last_error(None) or b"").decode())
+        self._h = h
+        self.devices = [int(d) for d in devices]
+        self.dim = 0
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.gsm_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != GSM_OK:
+            raise GsmError(rc, (self._lib.gsm_multi_last_error(self._h) or b"").decode())
+
+    def timings(self) -> dict:
+        t = MultiTimings()
+        self._check(self._lib.gsm_multi_get_timings(self._h, C.byref(t)))
+        return t.asdict()
+
+    def device_timings(self, i: int) -> dict:
+        t = Timings()
+        rc = self._lib.gsm_get_timings(self._lib.gsm_multi_context(self._h, int(i)), C.byref(t))
+        self._check(rc)
+        return t.asdict()
+
+    def summary(self) -> dict:
+        sm = Summary()
+        self._check(self._lib.gsm_multi_get_summary(self._h, C.byref(sm)))
+        return {k: getattr(sm, k) for k, _ in sm._fields_}
+
+    def set_option(self, key, value) -> None:
+        for i in range(len(self.devices)):
+            rc = self._lib.gsm_set_option(self._lib.gsm_multi_context(self._h, i), str(key).encode(), str(value).encode())
+            self._check(rc)
+
+    def slab(self, targets: Targets, i: int):
+        f, c = C.c_int64(), C.c_int64()
+        self._check(self._lib.gsm_multi_slab(self._h, C.byref(targets), int(i), C.byref(f), C.byref(c)))
+        return int(f.value), int(c.value)
+
+    def set_samples(self, coords, values):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        if coords.ndim == 1:
+            coords = coords[:, None]
+        n, dim = coords.shape
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        self._keep = (coords, values)
+        self._check(self._lib.gsm_multi_set_samples(self._h, _ptr(coords), int(dim), int(n), _ptr(values)))
+        self.dim, self.n = int(dim), int(n)
+
+    def set_samples_scaled(self, coords, values, scale_floor):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        if coords.ndim == 1:
+            coords = coords[:, None]
+        n, dim = coords.shape
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        if values.shape != (n,):
+            raise ValueError("values must have one entry per sample")
+        self._keep = (coords, values)
+        alpha, nan = C.c_double(0.0), C.c_int64(0)
+        self._check(self._lib.gsm_multi_set_samples_scaled(self._h, _ptr(coords), int(dim), int(n), _ptr(values),
+                                                           C.c_double(float(scale_floor)), C.byref(alpha), C.byref(nan)))
+        self.dim, self.n = int(dim), int(n)
+        return float(alpha.value), int(nan.value)
+
+    def local_krige(self, vario, model, targets, maxneighbors, minneighbors=1, radius=0.0, want_var=True,
+                    want_neighbors=False, out_mean=None, out_var=None, out_status=None):
+        if want_neighbors:
+            raise NotImplementedError("neighbour lists are a single-device test hook (Context.knn)")
+        M = Context.target_count(targets)
+        mean = _pool.empty(M, np.float64) if out_mean is None else out_mean
+        var = (_pool.empty(M, np.float64) if out_var is None else out_var) if want_var else None
+        status = _pool.empty(M, np.uint8) if out_status is None else out_status
+        o = NeighborOpts(int(maxneighbors), int(minneighbors), float(radius))
+        self._check(self._lib.gsm_multi_local_krige(self._h, C.byref(vario), C.byref(model), C.byref(targets), C.byref(o),
+                                                    _ptr(mean), _ptr(var), _ptr(status)))
+        return mean, var, status, None
+
+    def idw(self, exponent, targets, maxneighbors=0, minneighbors=1, radius=0.0, out_mean=None):
+        M = Context.target_count(targets)
+        mean = _pool.empty(M, np.float64) if out_mean is None else out_mean
+        status = _pool.empty(M, np.uint8)
+        o = NeighborOpts(int(maxneighbors), int(minneighbors), float(radius)) if maxneighbors != 0 else None
+        self._check(self._lib.gsm_multi_idw(self._h, float(exponent), C.byref(targets),
+                                            C.byref(o) if o is not None else None, _ptr(mean), _ptr(status)))
+        return mean, status
+
+    def global_krige(self, vario, model, targets, want_var=True):
+        M = Context.target_count(targets)
+        mean = _pool.empty(M, np.float64)
+        var = _pool.empty(M, np.float64) if want_var else None
+        st = C.c_int32(0)
+        self._check(self._lib.gsm_multi_global_krige(self._h, C.byref(vario), C.byref(model), C.byref(targets),
+                                                     _ptr(mean), _ptr(var), C.byref(st)))
+        return mean, var, bool(st.value)
 
 
 class GlobalFit:

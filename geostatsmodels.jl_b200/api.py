@@ -23,7 +23,7 @@ from . import _lib
 __all__ = [
     "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "PointSet", "CartesianGrid", "GeoTable",
     "georef", "IDW", "NN", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
-    "predict", "predictprob", "status", "fitpredict", "default_context", "set_default_device",
+    "predict", "predictprob", "status", "fitpredict", "default_context", "multi_context", "set_default_device",
 ]
 
 
@@ -282,6 +282,14 @@ def default_context(device: int | None = None) -> _lib.Context:
     return _CTX[dev]
 
 
+def multi_context(devices) -> "_lib.MultiContext":
+    """One cached multi-GPU handle per device list (gsm_multi_create: contexts + a warmed NCCL communicator)."""
+    key = tuple(int(d) for d in devices)
+    if key not in _CTX:
+        _CTX[key] = _lib.MultiContext(key)
+    return _CTX[key]
+
+
 # ---------------------------------------------------------------------------------------------
 # fit / predict / predictprob / status
 # ---------------------------------------------------------------------------------------------
@@ -401,13 +409,15 @@ def _targets_for(dom, alpha, first=0, count=-1):
 
 
 def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=True, minneighbors=1,
-               maxneighbors=10, neighborhood=None, distance="euclidean", device=None, first=0, count=-1,
-               ctx=None, out=None):
+               maxneighbors=10, neighborhood=None, distance="euclidean", device=None, devices=None, first=0,
+               count=-1, ctx=None, out=None):
     """fitpredict(model, geotable, domain; options) (models.jl:102-129).
 
     ``first``/``count`` (not in the reference) select a contiguous shard of the target index for
     multi-GPU runs: every rank predicts its slab of the same domain (models.jl:236-247 chunking).
-    ``out`` may hold preallocated (pinned) arrays ``mean`` / ``var`` / ``status`` the results DMA into."""
+    ``out`` may hold preallocated (pinned) arrays ``mean`` / ``var`` / ``status`` the results DMA into.
+    ``devices=[0, 1, ...]`` (not in the reference) runs the call on several GPUs of the box through the multi-GPU
+    C ABI (gsm_multi_*): samples replicated by one NCCL broadcast, target slabs, one host thread per device."""
     if not point:
         raise NotImplementedError("change of support (point=false) is not claimed by the GPU path")
     if distance != "euclidean":
@@ -420,7 +430,10 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         raise NotImplementedError("GPU path claims univariate tables only")
     z = np.asarray(data.table[names[0]], dtype=np.float64)
     X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
-    ctx = ctx or default_context(device)
+    if ctx is None and devices is not None and len(devices) > 1:
+        ctx = multi_context(devices)
+    ctx = ctx or default_context(device if devices is None else devices[0])
+    multi = isinstance(ctx, _lib.MultiContext)
     # _scale (models.jl:272-291) on the device: the raw coordinates are uploaded as they are (straight DMA when the
     # caller's arrays are page-locked), absmax / alpha / `dat |> Scale(alpha)` / the NaN check run as kernels
     r = model._range()
@@ -437,6 +450,8 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     if isinstance(model, NN):
         if prob:
             raise NotImplementedError("NN with prob=true (Dirac) is not claimed by the GPU path")
+        if multi:
+            raise NotImplementedError("NN is served by the single-device context")
         # nearest of the k nearest = nearest of all: the neighbourhood options do not change the result (nn.jl:47-54)
         col = ctx.nn(t, out=out.get("mean"))
     elif isinstance(model, IDW):
@@ -454,6 +469,9 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             mean, var, st, _ = ctx.local_krige(sm.fun._c(), sm._c(), t, _clamp_max(maxneighbors, len(z)),
                                                minneighbors, radius, want_var=prob, out_mean=out.get("mean"),
                                                out_var=out.get("var"), out_status=out.get("status"))
+        elif multi:
+            mean, var, fit_ok = ctx.global_krige(sm.fun._c(), sm._c(), t, want_var=prob)
+            st = np.zeros(M, dtype=np.uint8)
         else:
             gfit = ctx.global_fit(sm.fun._c(), sm._c())
             mean, var = gfit.predict(t, want_var=prob)

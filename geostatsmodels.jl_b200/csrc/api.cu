@@ -330,6 +330,7 @@ int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value) {
     else if (v == "pipe") ctx->opt_local_impl = GSM_IMPL_PIPE;
     else if (v == "simt") ctx->opt_local_impl = GSM_IMPL_SIMT;
     else if (v == "patch") ctx->opt_local_impl = GSM_IMPL_PATCH;
+    else if (v == "patch2") ctx->opt_local_impl = GSM_IMPL_PATCH2;
     else {
       gsm_set_error(ctx, "gsm_set_option: local_impl must be auto | patch | shr | pipe | simt");
       return GSM_ERR_INVALID;
@@ -338,6 +339,10 @@ int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value) {
   }
   if (k == "shr_smax") {
     ctx->opt_shr_smax = std::max(0, std::min(3, atoi(value)));
+    return GSM_OK;
+  }
+  if (k == "patch_nbmax") {
+    ctx->opt_patch_nbmax = atoi(value);
     return GSM_OK;
   }
   if (k == "bin_occupancy") {
@@ -373,17 +378,18 @@ int gsm_host_free(void* p) {
   return cudaFreeHost(p) == cudaSuccess ? GSM_OK : GSM_ERR_CUDA;
 }
 
-static int set_samples_impl(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values,
-                            bool scaled, double scale_floor, double* out_alpha, int64_t* out_nan) {
+}  // extern "C"
+
+// Phase 1 of gsm_set_samples[_scaled]: upload (and, when `scaled`, the reference's `_scale` on the device).
+// coords_dev / values_dev: when non-null the data already sit in ctx->coords / ctx->values (multi-GPU: they arrived
+// by NCCL broadcast) and nothing is uploaded.
+int gsm_upload_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values, bool scaled,
+                       double scale_floor, double* out_alpha, int64_t* out_nan) {
   if (!ctx) return GSM_ERR_INVALID;
   if (!coords || !values || dim < 1 || dim > 3 || n < 1) {
     gsm_set_error(ctx, "gsm_set_samples: need coords, values, 1 <= dim <= 3 and n >= 1");
     return GSM_ERR_INVALID;
   }
-  DeviceGuard g(ctx->device);
-  ctx->tim = gsm_timings{};
-  EventTimer et;
-  cudaEvent_t e0 = et.mark(ctx->stream);
   GSM_CHECK(gsm_reserve(ctx, ctx->coords, (size_t)n * dim * sizeof(double)));
   GSM_CHECK(gsm_reserve(ctx, ctx->values, (size_t)n * sizeof(double)));
   GSM_CUDA(ctx, cudaMemcpyAsync(ctx->coords.p, coords, (size_t)n * dim * sizeof(double), cudaMemcpyDefault, ctx->stream));
@@ -407,14 +413,30 @@ static int set_samples_impl(gsm_ctx* ctx, const double* coords, int32_t dim, int
     scale_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>((double*)ctx->coords.p, nc, alpha);
     ctx->tim.launches += 2;
   }
-  cudaEvent_t e1 = et.mark(ctx->stream);
+  return GSM_OK;
+}
+
+// Phase 2: the grid bins over ctx->coords / ctx->values (KNearestSearch construction, models.jl:155).
+int gsm_finish_samples(gsm_ctx* ctx, int32_t dim, int64_t n) {
   ctx->dim = dim;
   ctx->n = n;
   int rc = gsm_build_bins(ctx);
-  if (rc != GSM_OK) {
-    ctx->n = 0;
-    return rc;
-  }
+  if (rc != GSM_OK) ctx->n = 0;
+  return rc;
+}
+
+extern "C" {
+
+static int set_samples_impl(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values,
+                            bool scaled, double scale_floor, double* out_alpha, int64_t* out_nan) {
+  if (!ctx) return GSM_ERR_INVALID;
+  DeviceGuard g(ctx->device);
+  ctx->tim = gsm_timings{};
+  EventTimer et;
+  cudaEvent_t e0 = et.mark(ctx->stream);
+  GSM_CHECK(gsm_upload_samples(ctx, coords, dim, n, values, scaled, scale_floor, out_alpha, out_nan));
+  cudaEvent_t e1 = et.mark(ctx->stream);
+  GSM_CHECK(gsm_finish_samples(ctx, dim, n));
   cudaEvent_t e2 = et.mark(ctx->stream);
   GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->tim.h2d_ms = EventTimer::ms(e0, e1);

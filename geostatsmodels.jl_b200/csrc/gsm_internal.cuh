@@ -101,7 +101,7 @@ struct DevBuf {
 };
 
 // gsm_set_option(ctx, "local_impl", ...): which local-Kriging kernel serves k <= 32 (default: dispatch by shape)
-enum { GSM_IMPL_AUTO = 0, GSM_IMPL_SHR = 1, GSM_IMPL_PIPE = 2, GSM_IMPL_SIMT = 3, GSM_IMPL_PATCH = 4 };
+enum { GSM_IMPL_AUTO = 0, GSM_IMPL_SHR = 1, GSM_IMPL_PIPE = 2, GSM_IMPL_SIMT = 3, GSM_IMPL_PATCH = 4, GSM_IMPL_PATCH2 = 5 };
 
 struct gsm_ctx {
   int device = 0;
@@ -109,6 +109,7 @@ struct gsm_ctx {
   int opt_local_impl = GSM_IMPL_AUTO;
   int opt_shr_smax = 3;            // cap on the shared block columns of the shared-factor kernel
   double opt_bin_occupancy = 0.0;  // samples per bin cell of the neighbour search (0: default)
+  int opt_patch_nbmax = 0;         // block rows of the patch kernel's block store (0: default)
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // D2H overlap
   std::string err;
@@ -164,6 +165,9 @@ bool gsm_is_device_ptr(const void* p);
 // kernel launchers (each returns GSM_OK / GSM_ERR_*; all enqueue on ctx->stream)
 // ---------------------------------------------------------------------------------------------
 int gsm_build_bins(gsm_ctx* ctx);
+int gsm_upload_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values, bool scaled,
+                       double scale_floor, double* out_alpha, int64_t* out_nan);
+int gsm_finish_samples(gsm_ctx* ctx, int32_t dim, int64_t n);
 int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int* d_pos, int* d_cnt);
 int gsm_launch_knn_idw(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, double exponent, int minneighbors,
                        int* d_cnt, double* d_mean, unsigned char* d_status);
@@ -179,6 +183,9 @@ int gsm_launch_local_krige_pipe(gsm_ctx* ctx, const VarioDev& v, const ModelDev&
 int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                double* d_mean, double* d_var, unsigned char* d_status);
+int gsm_launch_local_krige_patch(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
+                                 const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                                 double* d_mean, double* d_var, unsigned char* d_status);
 int gsm_launch_local_krige_mid(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
                                const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
                                double* d_mean, double* d_var, unsigned char* d_status);

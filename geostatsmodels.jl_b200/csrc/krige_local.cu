@@ -289,6 +289,12 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   }
   int impl = ctx->opt_local_impl;
   if (impl == GSM_IMPL_AUTO) impl = (k > 8 && patches) ? GSM_IMPL_SHR : GSM_IMPL_PIPE;
+  if (impl == GSM_IMPL_PATCH || impl == GSM_IMPL_PATCH2) {
+    int rc = gsm_launch_local_krige_patch(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
+                                          d_status);
+    if (rc != GSM_ERR_UNSUPPORTED) return rc;
+    impl = GSM_IMPL_PIPE;
+  }
   if (impl == GSM_IMPL_SHR) {
     int rc = gsm_launch_local_krige_shr(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                         d_status);

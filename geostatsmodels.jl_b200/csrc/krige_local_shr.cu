@@ -178,14 +178,9 @@ job_index_kernel(TargetsDev tg, GroupMap gm, int k, int kmax, int smax, int minn
 
 }  // namespace
 
-int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
-                               const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
-                               double* d_mean, double* d_var, unsigned char* d_status) {
-  if (k > 32 || k < 1) return GSM_ERR_UNSUPPORTED;
-  if (tg.count <= 0) return GSM_OK;
-  if (tg.count >= (1LL << 31)) return GSM_ERR_UNSUPPORTED;   // descriptors hold 32-bit relative indices
-  const int nbc = k <= 8 ? 1 : (k <= 16 ? 2 : 4);
-  const bool d3 = ctx->dim >= 3;
+// Pool the neighbour lists of every patch of the launch: one 768-byte descriptor per job (krige_local_jobs.cuh).
+int gsm_build_jobs(gsm_ctx* ctx, const TargetsDev& tg, int k, int nbc, int smax, int minneighbors, const int* d_pos,
+                   const int* d_cnt, const JobIdx** out_jobs, long long* out_ngroups) {
   const GroupMap gm = gsm_make_group_map(tg);
   GSM_CHECK(gsm_reserve(ctx, ctx->job_idx, (size_t)gm.ngroups * sizeof(JobIdx)));
   JobIdx* jobs = (JobIdx*)ctx->job_idx.p;
@@ -198,13 +193,32 @@ int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& 
     }
   };
   mark();
-  int smax = nbc - 1;
-  smax = std::min(smax, ctx->opt_shr_smax);   // developer option "shr_smax": cap the sharing
   job_index_kernel<<<ixblocks, IX_WARPS * 32, 0, ctx->stream>>>(tg, gm, k, 8 * nbc, smax, minneighbors, d_pos, d_cnt, jobs);
   ctx->tim.launches++;
   mark();
   GSM_CUDA(ctx, cudaGetLastError());
-#define GSM_SHR_CALL(D, B) gsm_shr_entry_d##D##_b##B(ctx, v, m, ncon, centered, tg, jobs, gm.ngroups, k, d_pos, d_mean, d_var, d_status)
+  *out_jobs = jobs;
+  *out_ngroups = gm.ngroups;
+  return GSM_OK;
+}
+
+int gsm_launch_local_krige_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int centered,
+                               const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                               double* d_mean, double* d_var, unsigned char* d_status) {
+  if (k > 32 || k < 1) return GSM_ERR_UNSUPPORTED;
+  if (tg.count <= 0) return GSM_OK;
+  if (tg.count >= (1LL << 31)) return GSM_ERR_UNSUPPORTED;   // descriptors hold 32-bit relative indices
+  switch (ncon) {   // (instantiated constraint counts, krige_local_shr.cuh)
+    case 0: case 1: case 2: case 3: case 4: case 6: case 10: break;
+    default: return GSM_ERR_UNSUPPORTED;
+  }
+  const int nbc = k <= 8 ? 1 : (k <= 16 ? 2 : 4);
+  const bool d3 = ctx->dim >= 3;
+  const JobIdx* jobs = nullptr;
+  long long ngroups = 0;
+  const int smax = std::min(nbc - 1, ctx->opt_shr_smax);   // developer option "shr_smax": cap the sharing
+  GSM_CHECK(gsm_build_jobs(ctx, tg, k, nbc, smax, minneighbors, d_pos, d_cnt, &jobs, &ngroups));
+#define GSM_SHR_CALL(D, B) gsm_shr_entry_d##D##_b##B(ctx, v, m, ncon, centered, tg, jobs, ngroups, k, d_pos, d_mean, d_var, d_status)
   if (!d3) return nbc == 1 ? GSM_SHR_CALL(0, 1) : (nbc == 2 ? GSM_SHR_CALL(0, 2) : GSM_SHR_CALL(0, 4));
   return nbc == 1 ? GSM_SHR_CALL(1, 1) : (nbc == 2 ? GSM_SHR_CALL(1, 2) : GSM_SHR_CALL(1, 4));
 #undef GSM_SHR_CALL

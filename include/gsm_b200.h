@@ -191,6 +191,45 @@ GSM_API int gsm_idw(gsm_ctx* ctx, double exponent, const gsm_targets* targets, c
  * distances gives).  SURVEY section 8(f) "next" row; missing values are not claimed. */
 GSM_API int gsm_nn(gsm_ctx* ctx, const gsm_targets* targets, double* out_value);
 
+/* ---- multi-GPU: ONE caller drives all GPUs of a box (reference analogue: the contiguous
+ * index chunks of `_predictionthread!`, models.jl:236-247, one private fitted state per chunk, no exchange step).
+ * gsm_multi_create sets up one context per device and, for ndev > 1, an NCCL communicator (ncclCommInitAll, warmed
+ * once, cached in the handle; NCCL is bound at run time, so the single-GPU entry points do not depend on it).
+ * gsm_multi_set_samples[_scaled] uploads the samples ONCE to devices[0], replicates them with one ncclBroadcast over
+ * NVLink and builds the search bins on every device.  The predict calls split the selected target range
+ * [first, first + count) into ndev contiguous slabs (aligned to pairs of grid rows / planes so that no slab cuts a
+ * patch of the solve kernels), run one host thread per device and write every slab straight into the caller's HOST
+ * output arrays (pinned memory, gsm_host_alloc, makes that a direct DMA); no gather.  The handle is not re-entrant. */
+typedef struct gsm_multi gsm_multi;
+typedef struct gsm_multi_timings {
+  double upload_ms;    /* set_samples: host -> devices[0] (+ absmax / scale kernels)                 */
+  double bcast_ms;     /* set_samples: the NCCL broadcast (device time on devices[0]'s stream)       */
+  double bins_ms;      /* set_samples: bins on every device (host wall clock, devices in parallel)   */
+  double predict_ms;   /* last predict call: max over devices of gsm_timings.total_ms                */
+  double wall_ms;      /* last call: host wall clock                                                 */
+} gsm_multi_timings;
+GSM_API int gsm_multi_create(const int32_t* devices, int32_t ndev, gsm_multi** out);
+GSM_API int gsm_multi_destroy(gsm_multi* mg);
+GSM_API const char* gsm_multi_last_error(const gsm_multi* mg);   /* mg == NULL: last failed gsm_multi_create */
+GSM_API int gsm_multi_device_count(const gsm_multi* mg);
+GSM_API gsm_ctx* gsm_multi_context(gsm_multi* mg, int32_t i);    /* per-device context: timings, options */
+GSM_API int gsm_multi_get_timings(const gsm_multi* mg, gsm_multi_timings* out);
+GSM_API int gsm_multi_get_summary(const gsm_multi* mg, gsm_summary* out);   /* summed over the devices */
+GSM_API int gsm_multi_set_samples(gsm_multi* mg, const double* coords, int32_t dim, int64_t n, const double* values);
+GSM_API int gsm_multi_set_samples_scaled(gsm_multi* mg, const double* coords, int32_t dim, int64_t n, const double* values,
+                                 double scale_floor, double* out_alpha, int64_t* out_nan);
+/* the slab [out_first, out_first + out_count) device i predicts for this target descriptor */
+GSM_API int gsm_multi_slab(const gsm_multi* mg, const gsm_targets* targets, int32_t i, int64_t* out_first, int64_t* out_count);
+GSM_API int gsm_multi_local_krige(gsm_multi* mg, const gsm_variogram* vario, const gsm_model* model,
+                          const gsm_targets* targets, const gsm_neighbor_opts* opts, double* out_mean, double* out_var,
+                          uint8_t* out_status);
+GSM_API int gsm_multi_idw(gsm_multi* mg, double exponent, const gsm_targets* targets, const gsm_neighbor_opts* opts,
+                  double* out_mean, uint8_t* out_status);
+/* fitpredictfull: the factorisation is recomputed on every device, targets are split like above;
+ * out_fit_status: 1 = the factorisation succeeded everywhere (status(fitted), krig.jl:49-52) */
+GSM_API int gsm_multi_global_krige(gsm_multi* mg, const gsm_variogram* vario, const gsm_model* model,
+                           const gsm_targets* targets, double* out_mean, double* out_var, int32_t* out_fit_status);
+
 /* ---- measurement helper: sustained FP64 FMA throughput of this device in TFLOP/s (roofline peak) */
 GSM_API int gsm_measure_fp64_peak(gsm_ctx* ctx, double* out_dfma_tflops, double* out_dmma_tflops);
 

@@ -528,11 +528,15 @@ STEADY = [
 ]
 
 
+@pytest.mark.parametrize("impl", ["auto", "patch", "shr", "pipe"])
 @pytest.mark.parametrize("kind,dim,deg,k,dims,n,first,count,nbh", STEADY)
-def test_shared_factor_kernel_steady_state(gsm, oracle, kind, dim, deg, k, dims, n, first, count, nbh):
-    """Grids large enough that every CTA of the persistent shared-factor kernel runs many jobs (the 3-stage
-    shared-factor pipeline and the descriptor / pool streaming in steady state), against the C oracle."""
+def test_shared_factor_kernel_steady_state(gsm, oracle, kind, dim, deg, k, dims, n, first, count, nbh, impl):
+    """Grids large enough that every CTA of the persistent kernels runs many jobs (the 3-stage shared-factor
+    pipeline and the descriptor / pool streaming in steady state), against the C oracle -- through the default
+    dispatch and with every local-Kriging kernel forced (gsm_set_option "local_impl")."""
     import gsm_oracle_c as oc
+    if impl != "auto" and k > 32:
+        pytest.skip("k > 32 has one kernel")
     o = oracle
     ext = tuple(float(d) for d in dims)
     rng = np.random.default_rng(77 + dim + k)
@@ -554,7 +558,12 @@ def test_shared_factor_kernel_steady_state(gsm, oracle, kind, dim, deg, k, dims,
     grid = gsm.CartesianGrid(*dims)
     tab = gsm.georef({"z": z}, gsm.PointSet(X))
     kw["count"] = -1 if count is None else count
-    got = gsm.fitpredict(gm, tab, grid, neighborhood=nbh, **kw).z
+    c = gsm.Context(0)
+    c.set_option("local_impl", impl)
+    try:
+        got = gsm.fitpredict(gm, tab, grid, neighborhood=nbh, ctx=c, **kw).z
+    finally:
+        c.close()
     miss = np.ma.getmaskarray(got.mu) if np.ma.isMaskedArray(got.mu) else ~np.isfinite(got.mu)
     assert np.array_equal(miss, st != 0)
     ok = ~miss

@@ -1,34 +1,46 @@
 #!/usr/bin/env python
-"""A/B the local-Kriging kernels (GSM_LOCAL_IMPL) on the C3 workload: timings and element-wise differences."""
-import os, sys, numpy as np
+"""A/B the local-Kriging kernels (gsm_set_option local_impl) on a BASELINE workload: timings and differences.
+usage: ab_local.py [c3|ns|c4] impl [impl ...]"""
+import os, sys, time
+import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry
-gsm = entry.load_package(); L = gsm._lib
-import torch
-ny = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-n = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
-rng = np.random.default_rng(3)
-X = rng.uniform(0, 2048, size=(n, 2)); z = rng.standard_normal(n)
-ctx = gsm.Context(0); a = float(sys.argv[3]) if len(sys.argv) > 3 else 1 / 2048.0
-ctx.set_samples(X * a, z)
-v = L.make_variogram(1, 1.0, 0.1, 50 * a); m = L.make_model(1)
-t = gsm.Context.grid_targets((0, 0), (a, a), (2048, ny))
-M = 2048 * ny
-res = {}
-for impl in ("pipe", "shr"):
-    os.environ["GSM_LOCAL_IMPL"] = impl
-    om = torch.empty(M, dtype=torch.float64, device="cuda"); ov = torch.empty_like(om); ost = torch.empty(M, dtype=torch.uint8, device="cuda")
+gsm = entry.load_package()
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
+impls = sys.argv[2:] or ["shr", "patch"]
+if cfg == "c3":
+    rng = np.random.default_rng(3); n = 200_000
+    X = rng.uniform(0, 2048, size=(n, 2)); z = np.sin(X[:, 0] / 20) + np.cos(X[:, 1] / 30) + 0.1 * rng.standard_normal(n)
+    grid = gsm.CartesianGrid(2048, 2048)
+    model = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=50.0, sill=1.0, nugget=0.1))
+else:
+    rng = np.random.default_rng(6 if cfg == "ns" else 4); n = 1_000_000
+    X = rng.uniform(0, 256, size=(n, 3)); z = np.sin(X[:, 0] / 20) + np.cos(X[:, 2] / 30) + 0.1 * rng.standard_normal(n)
+    grid = gsm.CartesianGrid(256, 256, 256)
+    fun = gsm.SphericalVariogram(range=20.0, sill=1.0, nugget=0.1)
+    model = gsm.OrdinaryKriging(fun) if cfg == "ns" else gsm.UniversalKriging(fun, 2, 3)
+tab = gsm.georef({"z": z}, gsm.PointSet(X))
+ref = None
+for spec in impls:
+    impl, _, extra = spec.partition(":")
+    ctx = gsm.Context(0)
+    ctx.set_option("local_impl", impl)
+    for kv in filter(None, extra.split(",")):
+        key, _, val = kv.partition("=")
+        ctx.set_option(key, val)
+    best = None
     for _ in range(3):
-        ctx.local_krige(v, m, t, 32, out_mean=om, out_var=ov, out_status=ost)
-    print(impl, {k: round(x, 3) for k, x in ctx.timings().items() if k in ("knn_ms", "solve_ms")})
-    res[impl] = (om.cpu().numpy(), ov.cpu().numpy(), ost.cpu().numpy())
-a_, b_ = res["pipe"], res["shr"]
-dm = np.abs(a_[0] - b_[0]) / np.maximum(np.abs(a_[0]), 1e-9); dv = np.abs(a_[1] - b_[1]) / np.maximum(np.abs(a_[1]), 1e-12)
-bad = np.flatnonzero(~(dm < 1e-9) | ~(dv < 1e-9) | (a_[2] != b_[2]))
-print("max rel diff mean %.3e var %.3e; mismatches %d of %d; status!=0: pipe %d shr %d" % (np.nanmax(dm), np.nanmax(dv), bad.size, M, (a_[2] != 0).sum(), (b_[2] != 0).sum()))
-print("status values shr:", np.unique(b_[2], return_counts=True))
-if bad.size:
-    print("first bad:", bad[:24]); print("x:", bad[:24] % 2048, "y:", bad[:24] // 2048)
-    print("shr mean/var at bad:", b_[0][bad[:6]], b_[1][bad[:6]], "pipe:", a_[0][bad[:6]], a_[1][bad[:6]])
-    ys = np.unique(bad // 2048); print("bad rows:", ys[:40], "count rows", ys.size)
+        p = gsm.fitpredict(model, tab, grid, maxneighbors=32, prob=True, ctx=ctx).z
+        t = ctx.timings()
+        if best is None or t["solve_ms"] < best["solve_ms"]:
+            best = t
+    mu, var = np.array(p.mu), np.array(p.sigma)
+    line = f"{cfg} {spec:24s} knn {best['knn_ms']:7.2f} ms  index {best['index_ms']:6.2f} ms  solve {best['solve_ms']:8.2f} ms  nan {int(np.isnan(mu).sum())}"
+    if ref is not None:
+        line += f"  max|dmu| {np.nanmax(np.abs(mu - ref[0])):.2e}  max|dvar| {np.nanmax(np.abs(var - ref[1])):.2e}"
+    else:
+        ref = (mu, var)
+    print(line, flush=True)
+    ctx.close()
