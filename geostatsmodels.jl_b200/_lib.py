@@ -289,16 +289,18 @@ class Context:
         self._check(self._lib.gsm_set_samples(self._h, _ptr(coords), int(dim), int(n), _ptr(values)))
         self.dim, self.n = int(dim), int(n)
 
-    def set_samples_scaled(self, coords, values, scale_floor):
+    def set_samples_scaled(self, coords, values, scale_floor, dim=None, n=None):
         """Upload RAW coordinates; absmax, alpha = 1 / max(scale_floor, absmax) and the scaling happen on the device
-        (gsm_set_samples_scaled).  Returns (alpha, number of NaN values)."""
-        coords = np.ascontiguousarray(coords, dtype=np.float64)
-        if coords.ndim == 1:
-            coords = coords[:, None]
-        n, dim = coords.shape
-        values = np.ascontiguousarray(values, dtype=np.float64)
-        if values.shape != (n,):
-            raise ValueError("values must have one entry per sample")
+        (gsm_set_samples_scaled).  Returns (alpha, number of NaN values).  coords / values: numpy arrays, or device
+        pointers / torch CUDA tensors with dim and n (samples that arrived by a broadcast)."""
+        if isinstance(coords, np.ndarray):
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
+            if coords.ndim == 1:
+                coords = coords[:, None]
+            n, dim = coords.shape
+            values = np.ascontiguousarray(values, dtype=np.float64)
+            if values.shape != (n,):
+                raise ValueError("values must have one entry per sample")
         self._keep = (coords, values)
         alpha, nan = C.c_double(0.0), C.c_int64(0)
         self._check(self._lib.gsm_set_samples_scaled(self._h, _ptr(coords), int(dim), int(n), _ptr(values),

@@ -410,7 +410,7 @@ def _targets_for(dom, alpha, first=0, count=-1):
 
 def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=True, minneighbors=1,
                maxneighbors=10, neighborhood=None, distance="euclidean", device=None, devices=None, first=0,
-               count=-1, ctx=None, out=None):
+               count=-1, ctx=None, out=None, _device_samples=None):
     """fitpredict(model, geotable, domain; options) (models.jl:102-129).
 
     ``first``/``count`` (not in the reference) select a contiguous shard of the target index for
@@ -424,12 +424,18 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         raise NotImplementedError("only the Euclidean distance is claimed by the GPU path")
     if not isinstance(dom, (PointSet, CartesianGrid)):
         dom = PointSet(dom)
-    _checkcompat(model, data)
-    names = data.names()
-    if len(names) != 1:
-        raise NotImplementedError("GPU path claims univariate tables only")
-    z = np.asarray(data.table[names[0]], dtype=np.float64)
-    X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
+    if _device_samples is not None:
+        # (distributed.fitpredict_sharded) the samples already sit in device memory on this rank: an NCCL broadcast
+        # delivered them; `data` only carries the column name
+        coords_d, values_d, nobs, sdim, absmax_hint, names = _device_samples
+    else:
+        _checkcompat(model, data)
+        names = data.names()
+        if len(names) != 1:
+            raise NotImplementedError("GPU path claims univariate tables only")
+        z = np.asarray(data.table[names[0]], dtype=np.float64)
+        X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
+        nobs = len(z)
     if ctx is None and devices is not None and len(devices) > 1:
         ctx = multi_context(devices)
     ctx = ctx or default_context(device if devices is None else devices[0])
@@ -438,7 +444,10 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     # caller's arrays are page-locked), absmax / alpha / `dat |> Scale(alpha)` / the NaN check run as kernels
     r = model._range()
     floor = max(1.0 if math.isinf(r) else r, dom._absmax())
-    alpha, nnan = ctx.set_samples_scaled(X, z, floor)
+    if _device_samples is not None:
+        alpha, nnan = ctx.set_samples_scaled(coords_d, values_d, floor, dim=sdim, n=nobs)
+    else:
+        alpha, nnan = ctx.set_samples_scaled(X, z, floor)
     if nnan:
         raise NotImplementedError("missing values are not claimed by the GPU path")
     out = out or {}
@@ -458,7 +467,7 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         if prob:
             raise NotImplementedError("IDW with prob=true is not claimed by the GPU path")
         if neighbors:
-            mean, st = ctx.idw(model.exponent, t, maxneighbors=_clamp_max(maxneighbors, len(z)),
+            mean, st = ctx.idw(model.exponent, t, maxneighbors=_clamp_max(maxneighbors, nobs),
                                minneighbors=minneighbors, radius=radius)
         else:
             mean, st = ctx.idw(model.exponent, t)
@@ -466,7 +475,7 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     else:
         sm = model._scaled(alpha)
         if neighbors:
-            mean, var, st, _ = ctx.local_krige(sm.fun._c(), sm._c(), t, _clamp_max(maxneighbors, len(z)),
+            mean, var, st, _ = ctx.local_krige(sm.fun._c(), sm._c(), t, _clamp_max(maxneighbors, nobs),
                                                minneighbors, radius, want_var=prob, out_mean=out.get("mean"),
                                                out_var=out.get("var"), out_status=out.get("status"))
         elif multi:

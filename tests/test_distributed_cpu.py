@@ -27,6 +27,18 @@ def test_shard_partition_matches_index_chunks(gsm):
             assert sizes == sorted(sizes, reverse=True)   # the larger chunks come first
 
 
+def test_shard_units_keep_patch_boundaries(gsm):
+    sh, gu = gsm.distributed.shard, gsm.distributed.grid_unit
+    assert gu((256, 256, 256)) == 2 * 256 * 256 and gu((2048, 2048)) == 2 * 2048 and gu((17,)) == 1
+    for dims in ((256, 256, 256), (2048, 2048), (33, 21, 9), (100, 7)):
+        total, unit = int(np.prod(dims)), gu(dims)
+        for world in (1, 2, 3, 4, 8):
+            parts = [sh(total, r, world, unit) for r in range(world)]
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == total
+            for (f0, c0), (f1, _) in zip(parts, parts[1:]):
+                assert f0 + c0 == f1 and f1 % unit == 0
+
+
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, ROOT)
     import __graft_entry__ as entry

@@ -70,5 +70,6 @@ def test_multi_slabs_partition_idw_global_and_shards(gsm, oracle, ndev):
             assert np.allclose(a.mu, b.mu, rtol=1e-12, atol=1e-13) and np.allclose(a.sigma, b.sigma, rtol=1e-12, atol=1e-13)
         else:
             assert np.allclose(np.asarray(a), np.asarray(b), rtol=1e-12, atol=1e-13)
-    t = mc.timings()
-    assert t["wall_ms"] > 0 and (ndev == 1 or t["bcast_ms"] >= 0)
+    if ndev > 1:     # (a one-device list goes through the plain context)
+        t = mc.timings()
+        assert t["wall_ms"] > 0 and t["predict_ms"] > 0
