@@ -216,6 +216,15 @@ def other_configs(gsm, ctx, peak_tflops, reps=3):
             r["flops_per_prediction"] = fpp
         out[name] = r
 
+    # the reference's own (unreported) micro-benchmarks, benchmark/benchmarks.jl:25-26: OK GaussianVariogram(range=35),
+    # 3 samples -> 100 x 100 grid, neighbors=true, without and with a missing value
+    coords = np.array([[25.0, 25.0], [50.0, 75.0], [75.0, 50.0]])
+    okb = gsm.OrdinaryKriging(gsm.GaussianVariogram(range=35.0))
+    gridb = gsm.CartesianGrid(100, 100)
+    for nm, zz in (("kriging/full (benchmarks.jl:25)", [1.0, 2.0, 3.0]), ("kriging/miss (benchmarks.jl:26)", [np.nan, 2.0, 3.0])):
+        tabb = gsm.georef({"z": np.array(zz)}, gsm.PointSet(coords))
+        b, m, t = timed(lambda: gsm.fitpredict(okb, tabb, gridb, neighbors=True, ctx=ctx))
+        record(nm, 100 * 100, b, m, t)
     # C1: IDW (exponent 2), 10 k 2-D samples -> 256 x 256, all samples
     rng = np.random.default_rng(1)
     X = rng.uniform(0, 256, size=(10_000, 2))

@@ -23,7 +23,7 @@ from . import _lib
 __all__ = [
     "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "PointSet", "CartesianGrid", "GeoTable",
     "georef", "IDW", "NN", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
-    "predict", "predictprob", "status", "fitpredict", "default_context", "multi_context", "set_default_device",
+    "predict", "predictprob", "status", "fitpredict", "default_context", "multi_context", "set_default_device", "Dirac",
 ]
 
 
@@ -311,6 +311,52 @@ def _pointset_of(domain) -> np.ndarray:
     raise NotImplementedError("GPU path claims PointSet data only")
 
 
+def _values_of(data: "GeoTable", name) -> np.ndarray:
+    """Column as float64 with `missing` as NaN (None, numpy masked entries and NaN all mean missing)."""
+    col = data.table[name]
+    if np.ma.isMaskedArray(col):
+        return np.ma.filled(col.astype(np.float64), np.nan)
+    if isinstance(col, (list, tuple)) and any(c is None for c in col):
+        return np.array([np.nan if c is None else float(c) for c in col], dtype=np.float64)
+    return np.asarray(col, dtype=np.float64)
+
+
+def _drop_missing(model, X, z):
+    """Global fit with missing values (krig.jl:182-209 + 157-161): the zeroed rows / columns leave the reduced system
+    on the samples that have a value, and the untouched constraint rows of the missing samples force F_m nu = 0.
+    When F_m has full column rank (always for OrdinaryKriging; for UniversalKriging as soon as enough missing samples
+    are in general position) nu = 0: SimpleKriging with mean 0 on the reduced sample set.  SimpleKriging itself just
+    loses the missing samples."""
+    miss = np.isnan(z)
+    if not miss.any():
+        return model, X, z
+    keep = ~miss
+    if isinstance(model, SimpleKriging):
+        return model, X[keep], z[keep]
+    if isinstance(model, UniversalKriging):
+        F = np.ones((int(miss.sum()), len(model.exps)))
+        for q, e in enumerate(model.exps):
+            for d_, pw in enumerate(e):
+                F[:, q] *= X[miss][:, d_] ** pw
+        if np.linalg.matrix_rank(F) < len(model.exps):
+            raise NotImplementedError("global UniversalKriging with fewer missing samples (in general position) than "
+                                      "drift functions is not claimed by the GPU path")
+    return SimpleKriging(model.fun, 0.0), X[keep], z[keep]
+
+
+class Dirac:
+    """Distributions.Dirac: the predictive distribution of the deterministic models (idw.jl:57, nn.jl)."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def mean(self):
+        return self.value
+
+    def __repr__(self):
+        return f"Dirac(value={self.value!r})"
+
+
 class FittedKriging:
     def __init__(self, model, data, ctx, gfit, alpha=1.0):
         self.model, self.data, self._ctx, self._gfit, self._alpha = model, data, ctx, gfit, alpha
@@ -327,10 +373,13 @@ def fit(model, data: GeoTable, *, device=None, _alpha=1.0):
     ctx = _lib.Context(_DEFAULT_DEVICE if device is None else device)  # a fitted model owns its samples
     X = _pointset_of(data.domain) * _alpha if _alpha != 1.0 else _pointset_of(data.domain)
     var = data.names()[0]
-    ctx.set_samples(X, np.asarray(data.table[var], dtype=np.float64))
+    z = _values_of(data, var)
     if isinstance(model, IDW):
+        ctx.set_samples(X, z)
         return FittedIDW(model, data, ctx, _alpha)
-    m = model._scaled(_alpha) if _alpha != 1.0 else model
+    model_, X, z = _drop_missing(model, X, z)      # missing values: the reduced system (see _drop_missing)
+    ctx.set_samples(X, z)
+    m = model_._scaled(_alpha) if _alpha != 1.0 else model_
     gfit = ctx.global_fit(m.fun._c(), m._c())
     return FittedKriging(model, data, ctx, gfit, _alpha)
 
@@ -382,7 +431,9 @@ def predictprob(fitted, var, g):
     p = _as_point(g, fitted._ctx.dim) * fitted._alpha
     t = _lib.Context.point_targets(p)
     if isinstance(fitted, FittedIDW):
-        raise NotImplementedError("IDW predictprob (Dirac) is not claimed by the GPU path")
+        mean, _ = fitted._ctx.idw(fitted.model.exponent, t)      # predictprob = Dirac(predict) (idw.jl:57)
+        d = Dirac(float(mean[0]))
+        return d if scalar else [d]
     mean, var_ = fitted._gfit.predict(t, want_var=True)
     if var_[0] < 0:
         raise ValueError("DomainError: sqrt of negative variance")  # krig.jl:228
@@ -433,7 +484,7 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         names = data.names()
         if len(names) != 1:
             raise NotImplementedError("GPU path claims univariate tables only")
-        z = np.asarray(data.table[names[0]], dtype=np.float64)
+        z = _values_of(data, names[0])
         X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
         nobs = len(z)
     if ctx is None and devices is not None and len(devices) > 1:
@@ -444,12 +495,17 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     # caller's arrays are page-locked), absmax / alpha / `dat |> Scale(alpha)` / the NaN check run as kernels
     r = model._range()
     floor = max(1.0 if math.isinf(r) else r, dom._absmax())
+    kmodel = model
     if _device_samples is not None:
         alpha, nnan = ctx.set_samples_scaled(coords_d, values_d, floor, dim=sdim, n=nobs)
     else:
+        if not neighbors and isinstance(model, _KrigingModel) and np.isnan(z).any():
+            # fitpredictfull with missing values: the reduced system on the host side (alpha still from ALL samples)
+            floor = max(floor, float(np.abs(X).max()))
+            kmodel, X, z = _drop_missing(model, X, z)
         alpha, nnan = ctx.set_samples_scaled(X, z, floor)
-    if nnan:
-        raise NotImplementedError("missing values are not claimed by the GPU path")
+    if nnan and not (isinstance(model, _KrigingModel) and neighbors):
+        raise NotImplementedError("missing values are claimed for Kriging models only")
     out = out or {}
     t = _targets_for(dom, alpha, first, count)
     radius = 0.0
@@ -457,23 +513,30 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         radius = alpha * float(neighborhood)           # sneigh = alpha * neigh (models.jl:281), ball radius
     M = _lib.Context.target_count(t)
     if isinstance(model, NN):
-        if prob:
-            raise NotImplementedError("NN with prob=true (Dirac) is not claimed by the GPU path")
         if multi:
             raise NotImplementedError("NN is served by the single-device context")
-        # nearest of the k nearest = nearest of all: the neighbourhood options do not change the result (nn.jl:47-54)
+        # nearest of the k nearest = nearest of all (nn.jl:47-54) -- unless a ball neighbourhood leaves fewer than
+        # minneighbors samples inside the ball: that target is `missing` (models.jl:167-181)
         col = ctx.nn(t, out=out.get("mean"))
-    elif isinstance(model, IDW):
+        if neighbors and neighborhood is not None:
+            _, cnt = ctx.knn(t, _clamp_max(maxneighbors, nobs), radius)
+            kmax = _clamp_max(maxneighbors, nobs)
+            minn = 1 if (minneighbors > kmax or minneighbors < 1) else minneighbors
+            if (cnt < minn).any():
+                col = np.ma.masked_array(col, mask=cnt < minn)
         if prob:
-            raise NotImplementedError("IDW with prob=true is not claimed by the GPU path")
+            col = Dirac(col)                               # predictprob = Dirac(predict) (nn.jl)
+    elif isinstance(model, IDW):
         if neighbors:
             mean, st = ctx.idw(model.exponent, t, maxneighbors=_clamp_max(maxneighbors, nobs),
                                minneighbors=minneighbors, radius=radius)
         else:
             mean, st = ctx.idw(model.exponent, t)
         col = _mask_missing(mean, st)
+        if prob:
+            col = Dirac(col)                               # predictprob = Dirac(predict) (idw.jl:57)
     else:
-        sm = model._scaled(alpha)
+        sm = kmodel._scaled(alpha)
         if neighbors:
             mean, var, st, _ = ctx.local_krige(sm.fun._c(), sm._c(), t, _clamp_max(maxneighbors, nobs),
                                                minneighbors, radius, want_var=prob, out_mean=out.get("mean"),
@@ -481,10 +544,14 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         elif multi:
             mean, var, fit_ok = ctx.global_krige(sm.fun._c(), sm._c(), t, want_var=prob)
             st = np.zeros(M, dtype=np.uint8)
+            if not fit_ok:
+                st[:] = _lib.GSM_ST_SINGULAR           # status(fitted) == false (krig.jl:49-52)
         else:
             gfit = ctx.global_fit(sm.fun._c(), sm._c())
             mean, var = gfit.predict(t, want_var=prob)
             st = np.zeros(M, dtype=np.uint8)
+            if not gfit.status():
+                st[:] = _lib.GSM_ST_SINGULAR           # status(fitted) == false (krig.jl:49-52)
             gfit.close()
         # the library reduces the status / variance columns on the device (gsm_get_summary): the host only
         # scans them (tens of MB) when that is not available
@@ -495,7 +562,7 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             if known:
                 bad = sm["nonpositive_var"] > 0
             else:
-                bad = (var.min() <= 0) if clean else bool(np.any((var <= 0) & (st == 0)))
+                bad = bool(np.any(~(var > 0) & (st == 0)))     # (NaN counts as not positive)
             if bad:
                 raise ValueError("PosDefException: non-positive Kriging variance")  # MvNormal(mu, Sigma), krig.jl:236
             # Normal.(mean, var), models.jl:298-299

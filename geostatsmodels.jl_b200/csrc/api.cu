@@ -394,7 +394,8 @@ int gsm_upload_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t 
   GSM_CHECK(gsm_reserve(ctx, ctx->values, (size_t)n * sizeof(double)));
   GSM_CUDA(ctx, cudaMemcpyAsync(ctx->coords.p, coords, (size_t)n * dim * sizeof(double), cudaMemcpyDefault, ctx->stream));
   GSM_CUDA(ctx, cudaMemcpyAsync(ctx->values.p, values, (size_t)n * sizeof(double), cudaMemcpyDefault, ctx->stream));
-  if (scaled) {
+  {
+    // absmax of the coordinates (for `_scale`) and the number of missing values (NaN), reduced on the device
     GSM_CHECK(gsm_reserve(ctx, ctx->summ_dev, 4 * sizeof(unsigned long long)));
     unsigned long long* d = (unsigned long long*)ctx->summ_dev.p;
     GSM_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -404,14 +405,18 @@ int gsm_upload_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t 
     unsigned long long h[2] = {0, 0};
     GSM_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    double absmax;
-    static_assert(sizeof(double) == sizeof(unsigned long long), "bit cast");
-    memcpy(&absmax, &h[0], sizeof(double));
-    const double alpha = 1.0 / std::max(scale_floor, absmax);
-    if (out_alpha) *out_alpha = alpha;
+    ctx->n_missing = (long long)h[1];
     if (out_nan) *out_nan = (int64_t)h[1];
-    scale_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>((double*)ctx->coords.p, nc, alpha);
-    ctx->tim.launches += 2;
+    ctx->tim.launches += 1;
+    if (scaled) {
+      double absmax;
+      static_assert(sizeof(double) == sizeof(unsigned long long), "bit cast");
+      memcpy(&absmax, &h[0], sizeof(double));
+      const double alpha = 1.0 / std::max(scale_floor, absmax);
+      if (out_alpha) *out_alpha = alpha;
+      scale_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>((double*)ctx->coords.p, nc, alpha);
+      ctx->tim.launches += 1;
+    }
   }
   return GSM_OK;
 }
@@ -502,6 +507,10 @@ static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, co
       gsm_set_error(ctx, "out_mean is required");
       return GSM_ERR_INVALID;
     }
+  }
+  if (ctx->n_missing > 0 && mode == 2) {
+    gsm_set_error(ctx, "IDW with missing values is not claimed by the GPU path");
+    return GSM_ERR_UNSUPPORTED;
   }
   int maxn, minn;
   clamp_neighbors(ctx->n, opts, maxn, minn);
@@ -636,6 +645,10 @@ int gsm_nn(gsm_ctx* ctx, const gsm_targets* targets, double* out_value) {
   if (ctx->n <= 0) {
     gsm_set_error(ctx, "no samples: call gsm_set_samples first");
     return GSM_ERR_NO_SAMPLES;
+  }
+  if (ctx->n_missing > 0) {
+    gsm_set_error(ctx, "NN with missing values is not claimed by the GPU path");
+    return GSM_ERR_UNSUPPORTED;
   }
   DeviceGuard g(ctx->device);
   ctx->tim = gsm_timings{};

@@ -130,6 +130,7 @@ struct gsm_ctx {
   DevBuf red;         // small reduction scratch
   BinsDev bins{};
   double sample_mean = 0.0;
+  long long n_missing = 0;   // samples whose value is NaN (`missing`)
 
   // per-call scratch
   DevBuf nbr_pos;     // chunk x k int : positions into rec

@@ -440,6 +440,18 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
     gsm_set_error(ctx, "invalid Kriging model descriptor");
     return GSM_ERR_INVALID;
   }
+  if (model->kind == GSM_KRIG_UNIVERSAL)   // same validation as the neighbourhood entry points (universal.jl:56-57)
+    for (int a = 0; a < model->ndrift; ++a)
+      for (int c = 0; c < 3; ++c)
+        if (model->exps[a][c] < 0 || (c >= ctx->dim && model->exps[a][c] != 0)) {
+          gsm_set_error(ctx, "UniversalKriging: invalid monomial exponent");
+          return GSM_ERR_INVALID;
+        }
+  if (ctx->n_missing > 0) {
+    gsm_set_error(ctx, "global Kriging with missing values: drop the missing samples on the host (the reference's zeroed "
+                       "rows / columns are the reduced system; see the host mirror's fitpredict)");
+    return GSM_ERR_UNSUPPORTED;
+  }
   const long long n = ctx->n;
   if (n > 60000) {
     gsm_set_error(ctx, "global Kriging with more than 60000 samples does not fit the dense factor in HBM");

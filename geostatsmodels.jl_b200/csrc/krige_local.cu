@@ -31,7 +31,18 @@ struct WarpSmem {
   double px[32], py[32], pz[32];
 };
 
-template <int NCON>
+// MISS: samples whose value is NaN are `missing` (reference: missingindices / lhsmissings! / rhsmissings!,
+// krig.jl:182-209, 381-388, and the SVD minimum-norm solve of krig.jl:157-161).  The reference zeroes the covariance
+// rows / columns and right-hand-side entries of those samples but keeps their constraint entries.  Block by block
+// that system says (n = samples with a value, m = missing ones, F = drift matrix, nu = Lagrange multipliers):
+//     C_nn lambda_n + F_n nu = c_n ,    F_m nu = 0 ,    F_n' lambda_n + F_m' lambda_m = f0 .
+// lambda_m multiplies missing values and zeroed right-hand-side entries, so neither mean nor variance sees it; the
+// middle equation confines nu to null(F_m).  With nu = N y (N a basis of that null space) the prediction is the
+// usual block elimination on the samples that have a value with G, g, h replaced by N'GN, N'g, N'h -- for
+// OrdinaryKriging with any missing neighbour that is no constraint at all (SimpleKriging with mean 0), which is what
+// the reference's tests pin (test/krig.jl:284-312).  Whenever (lambda_n, nu) is unique this equals the reference's
+// minimum-norm solution; where it is not, the system is flagged singular.
+template <int NCON, bool MISS>
 __global__ void __launch_bounds__(LK_THREADS, 4)
 local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int minn, int centered,
                    const int* __restrict__ pos, const int* __restrict__ cnt, double* __restrict__ out_mean,
@@ -58,13 +69,19 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   gsm_target_coords(tg, tg.first + t, tx, ty, tz);
 
   // ---- gather ------------------------------------------------------------------------------
-  const bool live = lane < n;
+  bool live = lane < n;
   double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
   {
     int mypos = lane < k ? pos[t * (long long)k + lane] : -1;
     const int key = gsm_warp_sort_int(mypos < 0 ? 0x7fffffff : mypos, lane);   // canonical order
     if (live) r = b.rec[key];
   }
+  // a missing neighbour keeps its slot (padding row: sill on the diagonal, zeros elsewhere) and only contributes
+  // its drift row to F_m
+  const bool miss = MISS && live && (r.w != r.w);
+  const unsigned missmask = MISS ? __ballot_sync(0xffffffffu, miss) : 0u;
+  const bool nearby = live;          // neighbours that define the drift frame (missing ones included)
+  if (MISS && miss) live = false;
   sm.px[lane] = r.x;
   sm.py[lane] = r.y;
   sm.pz[lane] = r.z;
@@ -76,7 +93,7 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   for (int s = 1; s <= 16; ++s) {
     const int c = (lane + s) & 31;
     double val = 0.0;
-    if (live && c < n) {
+    if (live && c < n && !((missmask >> c) & 1u)) {
       const double dx = r.x - sm.px[c], dy = r.y - sm.py[c], dz = r.z - sm.pz[c];
       val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
     }
@@ -102,10 +119,11 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
     rhs[1] = live ? (NCON == 0 ? r.w - m.mean : r.w) : 0.0;
   }
   double f0[NCON > 0 ? NCON : 1];
+  double fm[(MISS && NCON > 0) ? NCON : 1];    // drift row of a missing neighbour
   if (NCON > 0) {
     double ox = 0.0, oy = 0.0, oz = 0.0, isc = 1.0;
     if (centered) {
-      double dmax = live ? d2t : 0.0;
+      double dmax = nearby ? d2t : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, gsm_shfl_xor(dmax, o));
       isc = dmax > 0.0 ? rsqrt(dmax) : 1.0;
@@ -117,7 +135,9 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
     const double gx = (tx - ox) * isc, gy = (ty - oy) * isc, gz = (tz - oz) * isc;
 #pragma unroll
     for (int q = 0; q < NCON; ++q) {
-      rhs[2 + q] = live ? gsm_drift(m, q, sx, sy, sz) : 0.0;
+      const double fq = gsm_drift(m, q, sx, sy, sz);
+      rhs[2 + q] = live ? fq : 0.0;
+      if (MISS) fm[q] = miss ? fq : 0.0;
       f0[q] = gsm_drift(m, q, gx, gy, gz);
     }
   }
@@ -169,6 +189,96 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
 #pragma unroll
       for (int q = 0; q <= p; ++q) G[p * NCON + q] = gsm_warp_sum(rhs[2 + p] * rhs[2 + q]);
     }
+    int nc = NCON;   // constraints left after the projection onto null(F_m)
+    if (MISS && missmask != 0u) {
+      // M = F_m' F_m; symmetric full-pivot Cholesky M[pi, pi] = [L1; L2][L1' L2'] finds its rank r and the null-space
+      // basis N[pi] = [-L1^-T L2'; I]; then G, g, h <- N'GN, N'g, N'h (every lane redundantly; local memory)
+      constexpr int NC1 = NCON > 0 ? NCON : 1;
+      double Mm[NC1 * NC1], Nb[NC1 * NC1], T1[NC1 * NC1];
+      int perm[NC1];
+      for (int a = 0; a < NCON; ++a) {
+        perm[a] = a;
+        for (int c = 0; c <= a; ++c) {
+          const double sacc = gsm_warp_sum(fm[a] * fm[c]);
+          Mm[a * NCON + c] = sacc;
+          Mm[c * NCON + a] = sacc;
+        }
+      }
+      double dmax0 = 0.0;
+      for (int a = 0; a < NCON; ++a) dmax0 = fmax(dmax0, Mm[a * NCON + a]);
+      int rk = 0;
+      for (; rk < NCON; ++rk) {
+        int piv = rk;
+        for (int a = rk + 1; a < NCON; ++a)
+          if (Mm[a * NCON + a] > Mm[piv * NCON + piv]) piv = a;
+        if (!(Mm[piv * NCON + piv] > 1e-12 * dmax0)) break;
+        if (piv != rk) {   // symmetric row / column swap
+          for (int a = 0; a < NCON; ++a) {
+            const double tmp = Mm[rk * NCON + a];
+            Mm[rk * NCON + a] = Mm[piv * NCON + a];
+            Mm[piv * NCON + a] = tmp;
+          }
+          for (int a = 0; a < NCON; ++a) {
+            const double tmp = Mm[a * NCON + rk];
+            Mm[a * NCON + rk] = Mm[a * NCON + piv];
+            Mm[a * NCON + piv] = tmp;
+          }
+          const int tp = perm[rk];
+          perm[rk] = perm[piv];
+          perm[piv] = tp;
+        }
+        const double dd = sqrt(Mm[rk * NCON + rk]);
+        Mm[rk * NCON + rk] = dd;
+        for (int a = rk + 1; a < NCON; ++a) Mm[a * NCON + rk] /= dd;
+        for (int a = rk + 1; a < NCON; ++a)
+          for (int c = rk + 1; c <= a; ++c) {
+            Mm[a * NCON + c] -= Mm[a * NCON + rk] * Mm[c * NCON + rk];
+            Mm[c * NCON + a] = Mm[a * NCON + c];
+          }
+      }
+      nc = NCON - rk;
+      // null-space basis, column q (q < nc): N[perm[rk + q]] = 1, N[perm[0..rk)] = -L1^-T (L2 row q)'
+      for (int q = 0; q < nc; ++q) {
+        for (int a = 0; a < NCON; ++a) Nb[a * NCON + q] = 0.0;
+        Nb[perm[rk + q] * NCON + q] = 1.0;
+        for (int a = rk - 1; a >= 0; --a) {      // back substitution with L1'
+          double sacc = -Mm[(rk + q) * NCON + a];
+          for (int c = a + 1; c < rk; ++c) sacc -= Mm[c * NCON + a] * Nb[perm[c] * NCON + q];
+          Nb[perm[a] * NCON + q] = sacc / Mm[a * NCON + a];
+        }
+      }
+      // T1 = G N (G symmetric, lower stored), then G <- N' T1, g <- N' g, hw <- N' hw
+      for (int a = 0; a < NCON; ++a)
+        for (int q = 0; q < nc; ++q) {
+          double sacc = 0.0;
+          for (int c = 0; c < NCON; ++c) sacc += (c <= a ? G[a * NCON + c] : G[c * NCON + a]) * Nb[c * NCON + q];
+          T1[a * NCON + q] = sacc;
+        }
+      double g2[NC1], h2[NC1];
+      for (int q = 0; q < nc; ++q) {
+        double sg = 0.0, sh = 0.0;
+        for (int a = 0; a < NCON; ++a) {
+          sg += Nb[a * NCON + q] * g[a];
+          sh += Nb[a * NCON + q] * hw[a];
+        }
+        g2[q] = sg;
+        h2[q] = sh;
+      }
+      for (int q = 0; q < nc; ++q)
+        for (int q2 = 0; q2 <= q; ++q2) {
+          double sacc = 0.0;
+          for (int a = 0; a < NCON; ++a) sacc += Nb[a * NCON + q] * T1[a * NCON + q2];
+          G[q * NCON + q2] = sacc;
+        }
+      for (int q = 0; q < NCON; ++q) {
+        g[q] = q < nc ? g2[q] : 0.0;
+        hw[q] = q < nc ? h2[q] : 0.0;
+      }
+      for (int q = nc; q < NCON; ++q) {   // inert rows: identity
+        for (int q2 = 0; q2 < q; ++q2) G[q * NCON + q2] = 0.0;
+        G[q * NCON + q] = 1.0;
+      }
+    }
     // Cholesky of G (every lane redundantly, registers), solve G nu = g
     double gd0[NCON > 0 ? NCON : 1];   // original diagonal: the singularity test is relative to it
 #pragma unroll
@@ -219,11 +329,11 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   }
 }
 
-template <int NCON>
+template <int NCON, bool MISS = false>
 int launch(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k, int minn, int centered,
            const int* pos, const int* cnt, double* mean, double* var, unsigned char* status) {
   long long blocks = (tg.count + LK_WARPS - 1) / LK_WARPS;
-  local_krige_kernel<NCON><<<(unsigned)blocks, LK_THREADS, 0, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
+  local_krige_kernel<NCON, MISS><<<(unsigned)blocks, LK_THREADS, 0, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
                                                                             pos, cnt, mean, var, status);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
@@ -263,6 +373,31 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool nonconst = false;
   for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
   const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
+  if (ctx->n_missing > 0) {
+    // samples with a missing value (NaN): the kernel that restates lhsmissings! / rhsmissings! / the SVD solve
+    if (k > 32) {
+      gsm_set_error(ctx, "missing values are claimed for maxneighbors <= 32 only");
+      return GSM_ERR_UNSUPPORTED;
+    }
+#define GSM_LKM_CASE(N) \
+  case N:               \
+    return launch<N, true>(ctx, v, m, tg, k, minneighbors, centered, d_pos, d_cnt, d_mean, d_var, d_status);
+    switch (ncon) {
+      GSM_LKM_CASE(0)
+      GSM_LKM_CASE(1)
+      GSM_LKM_CASE(2)
+      GSM_LKM_CASE(3)
+      GSM_LKM_CASE(4)
+      GSM_LKM_CASE(5)
+      GSM_LKM_CASE(6)
+      GSM_LKM_CASE(7)
+      GSM_LKM_CASE(8)
+      GSM_LKM_CASE(9)
+      GSM_LKM_CASE(10)
+    }
+#undef GSM_LKM_CASE
+    return GSM_ERR_UNSUPPORTED;
+  }
   if (k > 32)   // 32 < k <= 64: the matrix lives in shared memory (krige_local_mid.cu)
     return gsm_launch_local_krige_mid(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,
                                       d_status);

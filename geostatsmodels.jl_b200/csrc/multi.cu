@@ -199,6 +199,7 @@ int set_samples_multi(gsm_multi* mg, const double* coords, int32_t dim, int64_t 
     DevGuard g(c0->device);
     cudaEventRecord(ev[2], c0->stream);
   }
+  for (gsm_ctx* c : mg->ctx) c->n_missing = c0->n_missing;
   int rc = per_device(mg, [&](int i) -> int {
     gsm_ctx* c = mg->ctx[i];
     DevGuard g(c->device);

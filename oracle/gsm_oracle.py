@@ -168,7 +168,10 @@ VAR_EPS = 1e-10  # krig.jl:278-279
 
 
 class KrigingSystem:
-    """FittedKriging for a univariate model on point data without missing values."""
+    """FittedKriging for a univariate model on point data.  Missing values are NaN entries of z: the reference
+    finds them (missingindices, krig.jl:182-197), zeroes the rows and columns of those samples in the covariance
+    block (lhsmissings!, krig.jl:199-209; the constraint entries stay), zeroes their right-hand-side entries
+    (rhsmissings!, krig.jl:381-388), factors with an SVD (krig.jl:157-161) and drops them from the mean (krig.jl:261-262)."""
 
     def __init__(self, model: KrigingModel, X: np.ndarray, z: np.ndarray):
         self.model = model
@@ -177,10 +180,16 @@ class KrigingSystem:
         n = self.X.shape[0]
         m = n + model.ncon
         self.n, self.m = n, m
+        self.miss = np.flatnonzero(np.isnan(self.z))
         self.LHS = self._setlhs()
-        # bunchkaufman!(Symmetric(LHS), check=false)  == LAPACK dsytrf, uplo='U'
-        ldu, ipiv, info = lapack.dsytrf(self.LHS, lower=0)
-        self._ldu, self._ipiv, self.info = ldu, ipiv, info
+        if len(self.miss) == 0:
+            # bunchkaufman!(Symmetric(LHS), check=false)  == LAPACK dsytrf, uplo='U'
+            ldu, ipiv, info = lapack.dsytrf(self.LHS, lower=0)
+            self._ldu, self._ipiv, self.info = ldu, ipiv, info
+        else:
+            # svd!(LHS, alg=QRIteration())  == LAPACK dgesvd
+            self._U, self._S, self._Vt = np.linalg.svd(self.LHS, full_matrices=False)
+            self.info = 0   # _status(FHS::SVD) = true (krig.jl:52)
 
     def status(self) -> bool:  # krig.jl:49-52
         return self.info == 0
@@ -196,6 +205,9 @@ class KrigingSystem:
             F = drift_matrix(model.exps, X)
             LHS[n:, :n] = F.T
             LHS[:n, n:] = F
+        if len(self.miss):      # lhsmissings!: only the nfun x nfun block is knocked out
+            LHS[:n, self.miss] = 0.0
+            LHS[self.miss, :n] = 0.0
         return LHS
 
     def rhs(self, x0: np.ndarray) -> np.ndarray:  # krig.jl:342-361
@@ -206,11 +218,20 @@ class KrigingSystem:
             r[n] = 1.0
         elif model.kind == UK:
             r[n:] = drift_matrix(model.exps, x0[None, :])[0]
+        if len(self.miss):      # rhsmissings!
+            r[self.miss] = 0.0
         return r
 
     def weights(self, x0: np.ndarray):
         r = self.rhs(np.asarray(x0, dtype=np.float64))
-        w, info = lapack.dsytrs(self._ldu, self._ipiv, r, lower=0)  # FHS \ RHS
+        if len(self.miss) == 0:
+            w, info = lapack.dsytrs(self._ldu, self._ipiv, r, lower=0)  # FHS \ RHS
+        else:
+            # FHS \ RHS for an SVD (LinearAlgebra ldiv!(::SVD, b)): the minimum-norm least-squares solution over
+            # the singular values above eps(Float64) * S[1]
+            S = self._S
+            kk = int(np.sum(S > np.finfo(np.float64).eps * S[0]))
+            w = self._Vt[:kk].T @ ((self._U[:, :kk].T @ r) / S[:kk])
         return w, r
 
     def predict(self, x0):
@@ -218,10 +239,12 @@ class KrigingSystem:
         w, r = self.weights(x0)
         n = self.n
         lam, nu = w[:n], w[n:]
+        zz = np.where(np.isnan(self.z), 0.0, self.z)            # lambda (.) missing = 0 (krig.jl:261-262)
+        lam_v = np.where(np.isnan(self.z), 0.0, lam)
         if self.model.kind == SK:
-            mu = self.model.mean + float(np.sum(lam * (self.z - self.model.mean)))
+            mu = self.model.mean + float(np.sum(lam_v * (zz - self.model.mean)))
         else:
-            mu = float(np.sum(lam * self.z))
+            mu = float(np.sum(lam_v * zz))
         c0 = self.model.vario.sill - float(variogram(self.model.vario, 0.0))  # covzero for a point
         var = c0 - float(r[:n] @ lam) - float(r[n:] @ nu) + VAR_EPS
         return mu, var

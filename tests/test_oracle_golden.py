@@ -111,3 +111,23 @@ def test_knn_total_order_with_ties(oracle):
     idx = o.knn(X, np.array([0.0, 0.0]), 3)
     assert idx.tolist() == [0, 1, 2]  # four equidistant samples: lowest rows win
     assert o.knn(X, np.array([0.0, 0.0]), 5, radius=1.5).tolist() == [0, 1, 2, 3]
+
+
+def test_missing_data_reference_checks(oracle):
+    """test/krig.jl:284-312 "Missing data": z = [missing, 2, 3], GaussianVariogram(), target (50, 50):
+    SK / OK / DK means ~ 0 (atol 1e-6), 1 < UK(deg 1) mean < 2, all variances >= 0.  Pins the oracle's restatement of
+    missingindices / lhsmissings! / rhsmissings! / the SVD solve (krig.jl:157-161, 182-209, 261-262, 381-388)."""
+    o = oracle
+    P = np.array([[25.0, 25.0], [50.0, 75.0], [75.0, 50.0]])
+    z = np.array([np.nan, 2.0, 3.0])
+    g = o.Variogram(o.GAUSSIAN, 1.0, 0.0, 1.0)
+    x0 = np.array([50.0, 50.0])
+    res = {}
+    for name, m in (("sk", o.simple_kriging(g, 0.0)), ("ok", o.ordinary_kriging(g)), ("uk", o.universal_kriging(g, 1, 2)),
+                    ("dk", o.KrigingModel(o.UK, g, 0.0, ((0, 0),)))):
+        ks = o.KrigingSystem(m, P, z)
+        assert ks.status()                      # _status(FHS::SVD) = true
+        res[name] = ks.predict(x0)
+    assert abs(res["sk"][0]) < 1e-6 and abs(res["ok"][0]) < 1e-6 and abs(res["dk"][0]) < 1e-6
+    assert 1.0 < res["uk"][0] < 2.0
+    assert all(v[1] >= 0 for v in res.values())
