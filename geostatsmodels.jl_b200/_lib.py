@@ -17,6 +17,8 @@ GSM_MAX_NEIGHBORS = 64
 GSM_OK, GSM_ERR_INVALID, GSM_ERR_CUDA, GSM_ERR_NO_SAMPLES, GSM_ERR_UNSUPPORTED, GSM_ERR_SINGULAR = range(6)
 GSM_ST_OK, GSM_ST_MISSING, GSM_ST_SINGULAR = 0, 1, 2
 GSM_VARIO_GAUSSIAN, GSM_VARIO_SPHERICAL, GSM_VARIO_EXPONENTIAL = 0, 1, 2
+GSM_VARIO_CUBIC, GSM_VARIO_PENTASPHERICAL, GSM_VARIO_SINEHOLE, GSM_VARIO_CIRCULAR, GSM_VARIO_NUGGET = 3, 4, 5, 6, 7
+GSM_MAX_STRUCTURES = 4
 GSM_KRIG_SIMPLE, GSM_KRIG_ORDINARY, GSM_KRIG_UNIVERSAL = 0, 1, 2
 GSM_TARGETS_GRID, GSM_TARGETS_POINTS = 0, 1
 
@@ -31,9 +33,14 @@ EXPORTED_SYMBOLS = [
 ]
 
 
-class Variogram(C.Structure):
+class Structure(C.Structure):
     _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("sill", C.c_double), ("nugget", C.c_double),
-                ("range", C.c_double)]
+                ("range", C.c_double), ("metric", C.c_double * 9)]
+
+
+class Variogram(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nstruct", C.c_int32), ("sill", C.c_double), ("nugget", C.c_double),
+                ("range", C.c_double), ("structs", Structure * 4)]
 
 
 class Model(C.Structure):
@@ -540,7 +547,25 @@ class GlobalFit:
 
 
 def make_variogram(kind: int, sill: float, nugget: float, rng: float) -> Variogram:
-    return Variogram(int(kind), 0, float(sill), float(nugget), float(rng))
+    v = Variogram()
+    v.kind, v.nstruct, v.sill, v.nugget, v.range = int(kind), 0, float(sill), float(nugget), float(rng)
+    return v
+
+
+def make_composite_variogram(structs) -> Variogram:
+    """structs: iterable of (kind, sill, nugget, range, metric 3x3 or None)"""
+    structs = list(structs)
+    if not 1 <= len(structs) <= GSM_MAX_STRUCTURES:
+        raise ValueError("a composite variogram takes 1..4 structures")
+    v = Variogram()
+    v.kind, v.nstruct, v.sill, v.nugget, v.range = 0, len(structs), 0.0, 0.0, 1.0
+    for i, (kind, sill, nugget, rng, metric) in enumerate(structs):
+        s = v.structs[i]
+        s.kind, s.sill, s.nugget, s.range = int(kind), float(sill), float(nugget), float(rng)
+        m = np.eye(3) if metric is None else np.asarray(metric, dtype=np.float64).reshape(3, 3)
+        for e in range(9):
+            s.metric[e] = float(m.flat[e])
+    return v
 
 
 def make_model(kind: int, mean: float = 0.0, exps=()) -> Model:

@@ -21,7 +21,8 @@ import numpy as np
 from . import _lib
 
 __all__ = [
-    "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "PointSet", "CartesianGrid", "GeoTable",
+    "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "CubicVariogram", "PentasphericalVariogram",
+    "SineHoleVariogram", "CircularVariogram", "NuggetEffect", "CompositeVariogram", "PointSet", "CartesianGrid", "GeoTable",
     "georef", "IDW", "NN", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
     "predict", "predictprob", "status", "fitpredict", "default_context", "multi_context", "set_default_device", "Dirac",
 ]
@@ -30,18 +31,94 @@ __all__ = [
 # ---------------------------------------------------------------------------------------------
 # geostatistical functions (the GeoStatsFunctions subset the GPU path claims)
 # ---------------------------------------------------------------------------------------------
-@dataclass(frozen=True)
 class _Variogram:
-    sill: float = 1.0
-    range: float = 1.0
-    nugget: float = 0.0
+    """One GeoStatsFunctions variogram structure: family, total sill, nugget and a metric ball -- isotropic
+    (`range=r`) or anisotropic (`ranges=(r1, r2[, r3])` with an optional rotation matrix `rotation`, the columns being
+    the ball's principal axes: MetricBall(ranges, rotation))."""
     kind = -1
 
+    def __init__(self, sill=1.0, range=1.0, nugget=0.0, ranges=None, rotation=None):
+        self.sill, self.nugget = float(sill), float(nugget)
+        self.ranges = None if ranges is None else tuple(float(r) for r in ranges)
+        self.rotation = None if rotation is None else np.asarray(rotation, dtype=np.float64)
+        self.range = float(max(self.ranges)) if self.ranges is not None else float(range)   # range(fun): largest radius
+
+    def __eq__(self, other):
+        return type(self) is type(other) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def _key(self):
+        return (self.kind, self.sill, self.nugget, self.range, self.ranges,
+                None if self.rotation is None else tuple(self.rotation.ravel()))
+
     def scaled(self, alpha):
-        return type(self)(sill=self.sill, range=alpha * self.range, nugget=self.nugget)
+        """GeoStatsFunctions.scale(fun, alpha): the radii of the metric ball are multiplied by alpha."""
+        if self.ranges is None:
+            return type(self)(sill=self.sill, range=alpha * self.range, nugget=self.nugget)
+        return type(self)(sill=self.sill, nugget=self.nugget, ranges=tuple(alpha * r for r in self.ranges),
+                          rotation=self.rotation)
+
+    def _structure(self, coef=1.0):
+        """(kind, sill, nugget, range, metric) for the C descriptor; coef scales sill and nugget (c * gamma)."""
+        if self.ranges is None:
+            return (self.kind, coef * self.sill, coef * self.nugget, self.range, None)
+        d = len(self.ranges)
+        R = np.eye(3)
+        if self.rotation is not None:
+            R[:d, :d] = self.rotation[:d, :d]
+        inv = np.zeros(3)
+        inv[:d] = 1.0 / np.asarray(self.ranges)
+        return (self.kind, coef * self.sill, coef * self.nugget, 1.0, np.diag(inv) @ R.T)
+
+    def _structures(self):
+        return [self._structure()]
 
     def _c(self):
-        return _lib.make_variogram(self.kind, self.sill, self.nugget, self.range)
+        if self.ranges is None and self.kind <= _lib.GSM_VARIO_NUGGET:
+            return _lib.make_variogram(self.kind, self.sill, self.nugget, self.range)
+        return _lib.make_composite_variogram(self._structures())
+
+    # c * gamma and gamma1 + gamma2 (GeoStatsFunctions CompositeFunction: a sum of scaled structures)
+    def __rmul__(self, c):
+        return CompositeVariogram([(float(c), self)])
+
+    def __add__(self, other):
+        return CompositeVariogram([(1.0, self)]) + other
+
+
+class CompositeVariogram:
+    """Nested variogram sum_i c_i gamma_i (every structure with its own family, sill, nugget and metric ball)."""
+
+    def __init__(self, terms):
+        self.terms = [(float(c), f) for c, f in terms]
+        if not 1 <= len(self.terms) <= _lib.GSM_MAX_STRUCTURES:
+            raise ValueError("a composite variogram takes 1..4 structures")
+
+    @property
+    def range(self):       # range(fun): the largest radius over the structures
+        return max(f.range for _, f in self.terms)
+
+    @property
+    def sill(self):
+        return sum(c * f.sill for c, f in self.terms)
+
+    def scaled(self, alpha):
+        return CompositeVariogram([(c, f.scaled(alpha)) for c, f in self.terms])
+
+    def _structures(self):
+        return [f._structure(c) for c, f in self.terms]
+
+    def _c(self):
+        return _lib.make_composite_variogram(self._structures())
+
+    def __add__(self, other):
+        more = other.terms if isinstance(other, CompositeVariogram) else [(1.0, other)]
+        return CompositeVariogram(self.terms + list(more))
+
+    def __rmul__(self, c):
+        return CompositeVariogram([(float(c) * a, f) for a, f in self.terms])
 
 
 class GaussianVariogram(_Variogram):
@@ -54,6 +131,33 @@ class SphericalVariogram(_Variogram):
 
 class ExponentialVariogram(_Variogram):
     kind = _lib.GSM_VARIO_EXPONENTIAL
+
+
+class CubicVariogram(_Variogram):
+    kind = _lib.GSM_VARIO_CUBIC
+
+
+class PentasphericalVariogram(_Variogram):
+    kind = _lib.GSM_VARIO_PENTASPHERICAL
+
+
+class SineHoleVariogram(_Variogram):
+    kind = _lib.GSM_VARIO_SINEHOLE
+
+
+class CircularVariogram(_Variogram):
+    kind = _lib.GSM_VARIO_CIRCULAR
+
+
+class NuggetEffect(_Variogram):
+    """NuggetEffect(nugget): gamma(h) = (h > 0) nugget"""
+    kind = _lib.GSM_VARIO_NUGGET
+
+    def __init__(self, nugget=1.0, **kw):
+        super().__init__(sill=nugget, range=1.0, nugget=nugget)
+
+    def scaled(self, alpha):
+        return NuggetEffect(self.nugget)
 
 
 # ---------------------------------------------------------------------------------------------

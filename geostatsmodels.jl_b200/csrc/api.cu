@@ -58,14 +58,7 @@ struct DeviceGuard {
 
 VarioDev make_vario(const gsm_variogram& v) { return gsm_make_vario(v); }
 
-int check_vario(gsm_ctx* ctx, const gsm_variogram* v) {
-  if (!v || v->kind < GSM_VARIO_GAUSSIAN || v->kind > GSM_VARIO_EXPONENTIAL || !(v->range > 0.0) ||
-      !std::isfinite(v->range) || !std::isfinite(v->sill) || !std::isfinite(v->nugget)) {
-    gsm_set_error(ctx, "invalid variogram descriptor");
-    return GSM_ERR_INVALID;
-  }
-  return GSM_OK;
-}
+int check_vario(gsm_ctx* ctx, const gsm_variogram* v) { return gsm_check_vario(ctx, v); }
 
 int make_model(gsm_ctx* ctx, const gsm_model* m, int dim, ModelDev& d) {
   if (!m || m->kind < GSM_KRIG_SIMPLE || m->kind > GSM_KRIG_UNIVERSAL) {
@@ -379,6 +372,24 @@ int gsm_host_free(void* p) {
 }
 
 }  // extern "C"
+
+int gsm_check_vario(gsm_ctx* ctx, const gsm_variogram* v) {
+  bool ok = v != nullptr && v->nstruct >= 0 && v->nstruct <= GSM_MAX_STRUCTURES;
+  if (ok && v->nstruct == 0)
+    ok = v->kind >= GSM_VARIO_GAUSSIAN && v->kind <= GSM_VARIO_NUGGET && v->range > 0.0 && std::isfinite(v->range) &&
+         std::isfinite(v->sill) && std::isfinite(v->nugget);
+  for (int i = 0; ok && i < v->nstruct; ++i) {
+    const gsm_structure& s = v->structs[i];
+    ok = s.kind >= GSM_VARIO_GAUSSIAN && s.kind <= GSM_VARIO_NUGGET && s.range > 0.0 && std::isfinite(s.range) &&
+         std::isfinite(s.sill) && std::isfinite(s.nugget);
+    for (int e = 0; ok && e < 9; ++e) ok = std::isfinite(s.metric[e]);
+  }
+  if (!ok) {
+    gsm_set_error(ctx, "invalid variogram descriptor");
+    return GSM_ERR_INVALID;
+  }
+  return GSM_OK;
+}
 
 // Phase 1 of gsm_set_samples[_scaled]: upload (and, when `scaled`, the reference's `_scale` on the device).
 // coords_dev / values_dev: when non-null the data already sit in ctx->coords / ctx->values (multi-GPU: they arrived

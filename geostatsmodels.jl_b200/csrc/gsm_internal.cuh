@@ -41,18 +41,26 @@ void gsm_set_error(gsm_ctx* ctx, const std::string& msg);
 // ---------------------------------------------------------------------------------------------
 // device-side POD parameter blocks (passed by value as kernel arguments)
 // ---------------------------------------------------------------------------------------------
+struct VarioStruct {   // one structure of a general (composite / anisotropic / new-family) variogram
+  int kind;
+  double cs, nadd;       // partial sill and the nugget added for h > 0
+  double m[9];           // metric / range: t = |m (x - y)|
+};
 struct VarioDev {
   int kind;
   double sill, nugget, range, inv_range;
   double cs;    // partial sill: sill - nadd
   double nadd;  // nugget added for h > 0 (Gaussian: nugget + 1e-6)
+  int general;  // 1: evaluate through st[] (gsm_cov_vec); the fast kernels only take general == 0
+  int nstruct;
+  VarioStruct st[GSM_MAX_STRUCTURES];
 };
 
 // The ONE place where a variogram descriptor becomes device constants (include/gsm_b200.h lists the formulas).
 // GaussianVariogram replaces the nugget by n' = nugget + 1e-6 BEFORE forming the partial sill:
 // gamma(h) = (sill - n')(1 - exp(-3 t^2)) + (h > 0) n'  (oracle GAUSSIAN_NUGGET_EPS).
 inline VarioDev gsm_make_vario(const gsm_variogram& v) {
-  VarioDev d;
+  VarioDev d{};
   d.kind = v.kind;
   d.sill = v.sill;
   d.nugget = v.nugget;
@@ -60,6 +68,32 @@ inline VarioDev gsm_make_vario(const gsm_variogram& v) {
   d.inv_range = 1.0 / v.range;
   d.nadd = v.kind == GSM_VARIO_GAUSSIAN ? v.nugget + 1e-6 : v.nugget;
   d.cs = v.sill - d.nadd;
+  d.general = (v.nstruct > 0 || v.kind > GSM_VARIO_EXPONENTIAL) ? 1 : 0;
+  d.nstruct = 0;
+  if (d.general) {
+    const int ns = v.nstruct > 0 ? v.nstruct : 1;
+    d.nstruct = ns;
+    double total = 0.0;
+    for (int i = 0; i < ns; ++i) {
+      gsm_structure s{};
+      if (v.nstruct > 0) {
+        s = v.structs[i];
+      } else {   // a single isotropic structure of one of the newer families
+        s.kind = v.kind;
+        s.sill = v.sill;
+        s.nugget = v.nugget;
+        s.range = v.range;
+        s.metric[0] = s.metric[4] = s.metric[8] = 1.0;
+      }
+      VarioStruct& q = d.st[i];
+      q.kind = s.kind;
+      q.nadd = s.kind == GSM_VARIO_GAUSSIAN ? s.nugget + 1e-6 : s.nugget;
+      q.cs = s.kind == GSM_VARIO_NUGGET ? 0.0 : s.sill - q.nadd;
+      for (int e = 0; e < 9; ++e) q.m[e] = s.metric[e] / s.range;
+      total += s.kind == GSM_VARIO_NUGGET ? s.nugget : s.sill;
+    }
+    d.sill = total;   // covariance form: total sill - gamma
+  }
   return d;
 }
 
@@ -166,6 +200,7 @@ bool gsm_is_device_ptr(const void* p);
 // kernel launchers (each returns GSM_OK / GSM_ERR_*; all enqueue on ctx->stream)
 // ---------------------------------------------------------------------------------------------
 int gsm_build_bins(gsm_ctx* ctx);
+int gsm_check_vario(gsm_ctx* ctx, const gsm_variogram* v);
 int gsm_upload_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values, bool scaled,
                        double scale_floor, double* out_alpha, int64_t* out_nan);
 int gsm_finish_samples(gsm_ctx* ctx, int32_t dim, int64_t n);
@@ -258,6 +293,42 @@ __device__ __forceinline__ double gsm_cov_d2(const VarioDev& v, double d2) {
     g = v.cs * (1.0 - exp(-3.0 * t));
   }
   return v.sill - (g + v.nadd);
+}
+
+// General covariance sill - sum_i gamma_i(|m_i (dx, dy, dz)|): composite / anisotropic / newer families.
+static __device__ __noinline__ double gsm_cov_general(const VarioDev& v, double dx, double dy, double dz) {
+  double g = 0.0;
+  bool zero = true;
+  for (int i = 0; i < v.nstruct; ++i) {
+    const VarioStruct& s = v.st[i];
+    const double ux = s.m[0] * dx + s.m[1] * dy + s.m[2] * dz;
+    const double uy = s.m[3] * dx + s.m[4] * dy + s.m[5] * dz;
+    const double uz = s.m[6] * dx + s.m[7] * dy + s.m[8] * dz;
+    const double t2 = ux * ux + uy * uy + uz * uz;
+    if (!(t2 > 0.0)) continue;   // gamma_i(0) = 0
+    zero = false;
+    const double t = sqrt(t2);
+    double f;
+    switch (s.kind) {
+      case GSM_VARIO_GAUSSIAN: f = 1.0 - exp(-3.0 * t2); break;
+      case GSM_VARIO_SPHERICAL: f = t < 1.0 ? 1.5 * t - 0.5 * (t * t2) : 1.0; break;
+      case GSM_VARIO_EXPONENTIAL: f = 1.0 - exp(-3.0 * t); break;
+      case GSM_VARIO_CUBIC: f = t < 1.0 ? t2 * (7.0 + t * (-8.75 + t2 * (3.5 - 0.75 * t2))) : 1.0; break;
+      case GSM_VARIO_PENTASPHERICAL: f = t < 1.0 ? t * (1.875 + t2 * (-1.25 + 0.375 * t2)) : 1.0; break;
+      case GSM_VARIO_SINEHOLE: f = 1.0 - sin(M_PI * t) / (M_PI * t); break;
+      case GSM_VARIO_CIRCULAR: f = t < 1.0 ? 1.0 - (2.0 / M_PI) * acos(t) + (2.0 * t / M_PI) * sqrt(1.0 - t2) : 1.0; break;
+      default: f = 0.0; break;   // GSM_VARIO_NUGGET
+    }
+    g += s.cs * f + s.nadd;
+  }
+  (void)zero;
+  return v.sill - g;
+}
+// Covariance between two points from their coordinate difference: the three isotropic single-structure families
+// from the squared distance, everything else through gsm_cov_general.
+__device__ __forceinline__ double gsm_cov_vec(const VarioDev& v, double dx, double dy, double dz) {
+  if (v.general) return gsm_cov_general(v, dx, dy, dz);
+  return gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
 }
 
 __device__ __forceinline__ double gsm_ipow(double x, int p) {

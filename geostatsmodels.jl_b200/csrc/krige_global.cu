@@ -46,7 +46,7 @@ __global__ void cov_matrix_kernel(const double* __restrict__ px, const double* _
     val = v.sill;
   } else {
     const double dx = px[i] - px[j], dy = py[i] - py[j], dz = pz[i] - pz[j];
-    val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+    val = gsm_cov_vec(v, dx, dy, dz);
   }
   C[(size_t)j * np + i] = val;
 }
@@ -243,7 +243,7 @@ global_r_kernel(GlobalDev gd, VarioDev v, TargetsDev tg, long long t0, int mb, d
     double r = 0.0;
     if (s < gd.n && tlive) {
       const double dx = gd.px[s] - tx, dy = gd.py[s] - ty, dz = gd.pz[s] - tz;
-      r = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+      r = gsm_cov_vec(v, dx, dy, dz);
       for (int c = 0; c <= gd.ncon; ++c) acc[c] = fma(gd.D[(size_t)c * gd.np + s], r, acc[c]);
     }
     R[(size_t)s * mb + n] = r;
@@ -431,10 +431,7 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
     gsm_set_error(ctx, "no samples: call gsm_set_samples first");
     return GSM_ERR_NO_SAMPLES;
   }
-  if (!vario || vario->kind < 0 || vario->kind > 2 || !(vario->range > 0)) {
-    gsm_set_error(ctx, "invalid variogram descriptor");
-    return GSM_ERR_INVALID;
-  }
+  GSM_CHECK(gsm_check_vario(ctx, vario));
   if (!model || model->kind < 0 || model->kind > 2 ||
       (model->kind == GSM_KRIG_UNIVERSAL && (model->ndrift < 1 || model->ndrift > GSM_MAX_DRIFT))) {
     gsm_set_error(ctx, "invalid Kriging model descriptor");

@@ -95,7 +95,7 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
     double val = 0.0;
     if (live && c < n && !((missmask >> c) & 1u)) {
       const double dx = r.x - sm.px[c], dy = r.y - sm.py[c], dz = r.z - sm.pz[c];
-      val = gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+      val = gsm_cov_vec(v, dx, dy, dz);
     }
     sm.C[lane * LK_LD + c] = val;
     sm.C[c * LK_LD + lane] = val;
@@ -115,7 +115,7 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   {
     const double dx = r.x - tx, dy = r.y - ty, dz = r.z - tz;
     d2t = dx * dx + dy * dy + dz * dz;
-    rhs[0] = live ? gsm_cov_d2(v, d2t) : 0.0;
+    rhs[0] = live ? gsm_cov_vec(v, dx, dy, dz) : 0.0;
     rhs[1] = live ? (NCON == 0 ? r.w - m.mean : r.w) : 0.0;
   }
   double f0[NCON > 0 ? NCON : 1];
@@ -423,6 +423,7 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
     }
   }
   int impl = ctx->opt_local_impl;
+  if (v.general) impl = GSM_IMPL_SIMT;   // composite / anisotropic / newer families: the general covariance function
   if (impl == GSM_IMPL_AUTO) impl = (k > 8 && patches) ? GSM_IMPL_SHR : GSM_IMPL_PIPE;
   if (impl == GSM_IMPL_PATCH || impl == GSM_IMPL_PATCH2) {
     int rc = gsm_launch_local_krige_patch(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,

@@ -169,7 +169,7 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
             val = v.sill;
             if (row != col) {
               const double dx = S.px[row] - S.px[col], dy = S.py[row] - S.py[col], dz = S.pz[row] - S.pz[col];
-              val = gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+              val = v.general ? gsm_cov_general(v, dx, dy, dz) : gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
             }
           }
           e[s] = val;
@@ -189,7 +189,7 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
           if (q < nr && c < n) {
             if (q == 0) {
               const double dx = S.px[c] - tx, dy = S.py[c] - ty, dz = S.pz[c] - tz;
-              val = gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+              val = v.general ? gsm_cov_general(v, dx, dy, dz) : gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
             } else if (q == 1) {
               val = (m.kind == GSM_KRIG_SIMPLE) ? S.pv[c] - m.mean : S.pv[c];
             } else {

@@ -28,10 +28,11 @@ extern "C" {
 #define GSM_API
 #endif
 
-#define GSM_ABI_VERSION 1
+#define GSM_ABI_VERSION 2
 #define GSM_MAX_DIM 3
 #define GSM_MAX_DRIFT 10   /* UniversalKriging(fun, deg=2, dim=3) -> 10 monomials (universal.jl:54-77) */
 #define GSM_MAX_NEIGHBORS 64
+#define GSM_MAX_STRUCTURES 4   /* nested structures of a composite variogram */
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -57,14 +58,39 @@ enum {
  *   GAUSSIAN     (sill-n')(1-exp(-3t^2)) + (h>0) n',  n' = nugget + 1e-6 (the floor replaces the nugget everywhere)
  *   SPHERICAL    (sill-nugget)(1.5t-0.5t^3) for h<range, (sill-nugget) otherwise, + (h>0) nugget
  *   EXPONENTIAL  (sill-nugget)(1-exp(-3t)) + (h>0) nugget
- * The system is assembled in covariance form sill - gamma(h) (krig.jl:165-179, 364-378). */
-enum { GSM_VARIO_GAUSSIAN = 0, GSM_VARIO_SPHERICAL = 1, GSM_VARIO_EXPONENTIAL = 2 };
-typedef struct gsm_variogram {
+ *   CUBIC        (sill-nugget)(7t^2 - 8.75t^3 + 3.5t^5 - 0.75t^7) for t<1, (sill-nugget) otherwise, + (h>0) nugget
+ *   PENTASPHERICAL (sill-nugget)(1.875t - 1.25t^3 + 0.375t^5) for t<1, (sill-nugget) otherwise, + (h>0) nugget
+ *   SINEHOLE     (sill-nugget)(1 - sin(pi t)/(pi t)) + (h>0) nugget
+ *   CIRCULAR     (sill-nugget)(1 - (2/pi) acos(t) + (2t/pi) sqrt(1-t^2)) for t<1, (sill-nugget) otherwise, + (h>0) nugget
+ *   NUGGET       (h>0) nugget   (NuggetEffect; sill = nugget)
+ * The system is assembled in covariance form sill - gamma(h) (krig.jl:165-179, 364-378).
+ *
+ * nstruct == 0: one isotropic structure described by kind / sill / nugget / range (the round-1 layout; the first 32
+ * bytes are unchanged).  nstruct >= 1: a composite (nested) variogram gamma = sum_i gamma_i (GeoStatsFunctions
+ * CompositeFunction, "sum of structures", comment at krig.jl:147); every structure has its own family, total sill,
+ * nugget and metric ball: t_i = |metric_i (x - y)| / range_i with `metric` a row-major 3 x 3 matrix -- the identity for
+ * an isotropic ball, diag(1/r_1, 1/r_2, 1/r_3) R' with range = 1 for an anisotropic (Mahalanobis) ball with radii r and
+ * rotation R.  The top-level kind / sill / nugget / range are ignored then (total sill = sum of the structures' sills).
+ * The neighbour search stays Euclidean (`distance` of fitpredict, models.jl:112).  Composite / anisotropic / new-family
+ * variograms run on the general kernels (maxneighbors <= 64; the shared-factor fast path serves the three
+ * isotropic single-structure families above). */
+enum { GSM_VARIO_GAUSSIAN = 0, GSM_VARIO_SPHERICAL = 1, GSM_VARIO_EXPONENTIAL = 2, GSM_VARIO_CUBIC = 3,
+       GSM_VARIO_PENTASPHERICAL = 4, GSM_VARIO_SINEHOLE = 5, GSM_VARIO_CIRCULAR = 6, GSM_VARIO_NUGGET = 7 };
+typedef struct gsm_structure {
   int32_t kind;
   int32_t _pad;
-  double sill;    /* total sill                         */
+  double sill;        /* total sill of this structure (its nugget included) */
   double nugget;
-  double range;   /* ALREADY multiplied by alpha        */
+  double range;       /* ALREADY multiplied by alpha */
+  double metric[9];   /* row-major 3 x 3, see above */
+} gsm_structure;
+typedef struct gsm_variogram {
+  int32_t kind;
+  int32_t nstruct;  /* 0: the single isotropic structure below; 1..GSM_MAX_STRUCTURES: structs[] */
+  double sill;      /* total sill                         */
+  double nugget;
+  double range;     /* ALREADY multiplied by alpha        */
+  gsm_structure structs[GSM_MAX_STRUCTURES];
 } gsm_variogram;
 
 /* Kriging variant: SimpleKriging (simple.jl:29-69), OrdinaryKriging (ordinary.jl:25-77),

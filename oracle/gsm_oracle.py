@@ -41,7 +41,7 @@ from scipy.linalg import lapack
 # ----------------------------------------------------------------------------------------------
 # Variograms (GeoStatsFunctions 0.15, restated; call sites krig.jl:12,100,125,128,167,297,347)
 # ----------------------------------------------------------------------------------------------
-GAUSSIAN, SPHERICAL, EXPONENTIAL = 0, 1, 2
+GAUSSIAN, SPHERICAL, EXPONENTIAL, CUBIC, PENTASPHERICAL, SINEHOLE, CIRCULAR, NUGGET = 0, 1, 2, 3, 4, 5, 6, 7
 _KIND_NAMES = {"gaussian": GAUSSIAN, "spherical": SPHERICAL, "exponential": EXPONENTIAL}
 
 # GaussianVariogram adds a small epsilon to the nugget "for numerical stability" (restated from
@@ -55,14 +55,40 @@ GAUSSIAN_NUGGET_EPS = 1e-6
 
 @dataclass(frozen=True)
 class Variogram:
+    """One isotropic structure (kind, sill, nugget, range), or -- when `structs` is not empty -- a composite
+    (nested) variogram gamma = sum_i gamma_i with structs[i] = (kind, sill, nugget, range, metric): t_i =
+    |metric_i (x - y)| / range_i, metric a 3 x 3 matrix (None: identity); an anisotropic ball with radii r and
+    rotation R is metric = diag(1 / r) R', range = 1 (GeoStatsFunctions MetricBall / CompositeFunction, restated)."""
     kind: int
     sill: float = 1.0
     nugget: float = 0.0
     range: float = 1.0
+    structs: tuple = ()
 
     def scaled(self, alpha: float) -> "Variogram":
         # GeoStatsFunctions.scale(fun, alpha): the metric-ball radius is multiplied by alpha
-        return Variogram(self.kind, self.sill, self.nugget, alpha * self.range)
+        st = tuple((k, s, n, alpha * r, m) for k, s, n, r, m in self.structs)
+        return Variogram(self.kind, self.sill, self.nugget, alpha * self.range, st)
+
+    @property
+    def total_sill(self) -> float:
+        if not self.structs:
+            return self.sill
+        return float(sum(n if k == NUGGET else s for k, s, n, r, m in self.structs))
+
+    @property
+    def maxrange(self) -> float:
+        """range(fun): the largest radius (for `_scalefactor(model)`, models.jl:293-296)"""
+        if not self.structs:
+            return self.range
+        out = []
+        for k, s, n, r, m in self.structs:
+            if m is None:
+                out.append(r)
+            else:   # radii of the ball = range / singular values of the metric
+                sv = np.linalg.svd(np.asarray(m, dtype=np.float64).reshape(3, 3), compute_uv=False)
+                out.append(r / float(sv[sv > 0].min()))
+        return max(out)
 
 
 def variogram(v: Variogram, h):
@@ -80,7 +106,41 @@ def variogram(v: Variogram, h):
     if v.kind == EXPONENTIAL:
         t = h / r
         return (s - n) * (1.0 - np.exp(-3.0 * t)) + (h > 0) * n
+    t = h / r
+    if v.kind == CUBIC:
+        poly = (s - n) * (7.0 * t ** 2 - 8.75 * t ** 3 + 3.5 * t ** 5 - 0.75 * t ** 7)
+        return np.where(t < 1.0, poly, (s - n)) + (h > 0) * n
+    if v.kind == PENTASPHERICAL:
+        poly = (s - n) * (1.875 * t - 1.25 * t ** 3 + 0.375 * t ** 5)
+        return np.where(t < 1.0, poly, (s - n)) + (h > 0) * n
+    if v.kind == SINEHOLE:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            g = np.where(t > 0, 1.0 - np.sin(np.pi * t) / (np.pi * t), 0.0)
+        return (s - n) * g + (h > 0) * n
+    if v.kind == CIRCULAR:
+        tc = np.minimum(t, 1.0)
+        g = 1.0 - (2.0 / np.pi) * np.arccos(tc) + (2.0 * tc / np.pi) * np.sqrt(1.0 - tc * tc)
+        return np.where(t < 1.0, (s - n) * g, (s - n)) + (h > 0) * n
+    if v.kind == NUGGET:
+        return (h > 0) * n
     raise ValueError("unknown variogram kind")
+
+
+def cov_points(v: Variogram, A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """Covariance form sill - gamma between two point sets (rows): isotropic single structures from the Euclidean
+    distance matrix, composites structure by structure on the transformed coordinate differences."""
+    if not v.structs:
+        return covariance(v, pairdist(A, B))
+    dim = A.shape[1]
+    g = np.zeros((A.shape[0], B.shape[0]))
+    for kind, sill, nugget, rng, metric in v.structs:
+        M3 = np.eye(3) if metric is None else np.asarray(metric, dtype=np.float64).reshape(3, 3)
+        M = M3[:, :dim]
+        TA, TB = A @ M.T, B @ M.T
+        h = pairdist(TA, TB)
+        one = Variogram(kind, nugget if kind == NUGGET else sill, nugget, rng)
+        g = g + variogram(one, h)
+    return v.total_sill - g
 
 
 def covariance(v: Variogram, h):
@@ -197,7 +257,7 @@ class KrigingSystem:
     def _setlhs(self) -> np.ndarray:
         model, X, n, m = self.model, self.X, self.n, self.m
         LHS = np.zeros((m, m), order="F")
-        LHS[:n, :n] = covariance(model.vario, pairdist(X, X))  # pairwise! + lhsbanded!
+        LHS[:n, :n] = cov_points(model.vario, X, X)  # pairwise! + lhsbanded!
         if model.kind == OK:  # ordinary.jl:33-58
             LHS[n, :n] = 1.0
             LHS[:n, n] = 1.0
@@ -213,7 +273,7 @@ class KrigingSystem:
     def rhs(self, x0: np.ndarray) -> np.ndarray:  # krig.jl:342-361
         model, n, m = self.model, self.n, self.m
         r = np.zeros(m)
-        r[:n] = covariance(model.vario, pairdist(self.X, x0[None, :])[:, 0])
+        r[:n] = cov_points(model.vario, self.X, x0[None, :])[:, 0]
         if model.kind == OK:
             r[n] = 1.0
         elif model.kind == UK:
@@ -245,7 +305,7 @@ class KrigingSystem:
             mu = self.model.mean + float(np.sum(lam_v * (zz - self.model.mean)))
         else:
             mu = float(np.sum(lam_v * zz))
-        c0 = self.model.vario.sill - float(variogram(self.model.vario, 0.0))  # covzero for a point
+        c0 = self.model.vario.total_sill  # covzero for a point: sill - gamma(0) (krig.jl:295-301)
         var = c0 - float(r[:n] @ lam) - float(r[n:] @ nu) + VAR_EPS
         return mu, var
 
@@ -378,7 +438,7 @@ def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, 
     (fewer than minneighbors found, models.jl:178-181), 2 factorisation failed."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     z = np.asarray(z, dtype=np.float64)
-    rng = model.vario.range if isinstance(model, KrigingModel) else np.inf
+    rng = model.vario.maxrange if isinstance(model, KrigingModel) else np.inf
     alpha = scale_factor(rng, points_absmax(X), _dom_absmax(dom))
     smodel = model.scaled(alpha) if isinstance(model, KrigingModel) else model
     sX = X * alpha

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(gsm):
     lib = gsm._lib.load()
     for s in declared_symbols():
         assert hasattr(lib, s), s
-    assert lib.gsm_abi_version() == 1
+    assert lib.gsm_abi_version() == 2
 
 
 def test_struct_layouts_match_c(gsm, tmp_path):
