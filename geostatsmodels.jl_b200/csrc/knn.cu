@@ -32,8 +32,7 @@ struct Heap {
 
 // (d2a, rowa) < (d2b, rowb)?  Rows are only fetched on exact distance ties.
 __device__ __forceinline__ bool key_less(double da, int pa, double db, int pb, const int* __restrict__ sidx) {
-  if (da < db) return true;
-  if (da > db) return false;
+  if (da != db) return da < db;     // (exact distance ties are rare: lattice samples)
   return sidx[pa] < sidx[pb];
 }
 
@@ -126,6 +125,209 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
   }
   int cnt = 0;              // heap fill of the previous target (k when complete)
   double prev_worst = inf;  // its k-th squared distance
+
+  // ---- per-target epilogue: NN value, fused local IDW, or the neighbour list (heap order) -------------------
+  auto emit = [&](const long long t, const int cnt) {
+    if (idw.on && idw.mode < 0) {
+      // ---- NN model (nn.jl:47-54): the nearest sample's value; among equidistant samples the lowest row ----
+      int best = -1;
+      for (int i = 0; i < cnt; ++i)
+        if (best < 0 || key_less(hp.D(i), hp.P(i), hp.D(best), hp.P(best), sidx)) best = i;
+      idw.mean[t] = best >= 0 ? rec[hp.P(best)].w : __longlong_as_double(0x7ff8000000000000LL);
+      if (idw.status) idw.status[t] = best >= 0 ? GSM_ST_OK : GSM_ST_MISSING;
+      out_cnt[t] = cnt;
+      return;
+    }
+    if (idw.on) {
+      // ---- fused local IDW over the selected neighbours, in heap order (the order idw_local_kernel would see) ----
+      double sw = 0.0, swz = 0.0, hitv = 0.0;
+      int nkeep = 0, hitrow = 0x7fffffff;
+      for (int i = 0; i < cnt; ++i) {
+        const double d2 = hp.D(i);
+        if (radius > 0.0 && !(__dsqrt_rn(d2) <= radius)) continue;
+        nkeep++;
+        const int q = hp.P(i);
+        const double val = rec[q].w;
+        if (d2 > 0.0) {
+          const double w = gsm_idww::idw_weight_rt(idw.mode, d2, idw.e, idw.ei);
+          sw += w;
+          swz = fma(w, val, swz);
+        } else {   // exact hit: the FIRST such sample of the reference's ascending (d2, row) list = lowest row
+          const int rw = sidx[q];
+          if (rw < hitrow) {
+            hitrow = rw;
+            hitv = val;
+          }
+        }
+      }
+      out_cnt[t] = nkeep;
+      if (nkeep < idw.minn || nkeep <= 0) {
+        idw.mean[t] = __longlong_as_double(0x7ff8000000000000LL);
+        if (idw.status) idw.status[t] = GSM_ST_MISSING;
+      } else {
+        idw.mean[t] = hitrow != 0x7fffffff ? hitv : swz / sw;
+        if (idw.status) idw.status[t] = GSM_ST_OK;
+      }
+      return;
+    }
+    // ---- emit (heap order); KBallSearch keeps neighbours with distance <= radius (models.jl:158) ----
+    int* o = out_pos + t * (long long)k;
+    int nkeep = 0;
+    if (radius > 0.0) {
+      for (int i = 0; i < cnt; ++i)
+        if (__dsqrt_rn(hp.D(i)) <= radius) o[nkeep++] = hp.P(i);
+    } else {
+      for (int i = 0; i < cnt; ++i) o[i] = hp.P(i);
+      nkeep = cnt;
+    }
+    for (int i = nkeep; i < k; ++i) o[i] = -1;
+    out_cnt[t] = nkeep;
+  };
+
+  if (tiled != 0) {
+    // ---- grid targets: WARP-UNIFORM search.  The 32 targets of a warp form a compact brick, so their searches
+    // visit nearly the same cells.  Instead of 32 divergent ring walks, the warp walks ONE ring sequence around
+    // the brick's cell box; every candidate record is loaded once (a broadcast) and tested by all lanes against
+    // their own heap.  Cells are skipped / x-runs clipped with the brick's bounding box and the LARGEST current
+    // k-th distance of the warp (a candidate farther than that from the box is farther than every lane's k-th
+    // distance from its target).  A lane stops changing once its own k-th distance is inside the covered box; the
+    // warp stops when every lane has.
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool active = t0 < tg.count;
+    const unsigned am = __ballot_sync(FULL, active);
+    if (am == 0u) return;
+    double tx = 0.0, ty = 0.0, tz = 0.0;
+    if (active) gsm_target_coords(tg, tg.first + t0, tx, ty, tz);
+    {   // idle lanes shadow an active one: they neither widen the brick nor delay the end of the search
+      const int src = active ? lane : __ffs(am) - 1;
+      tx = __shfl_sync(FULL, tx, src);
+      ty = __shfl_sync(FULL, ty, src);
+      tz = __shfl_sync(FULL, tz, src);
+    }
+    const double tc[3] = {tx, ty, tz};
+    int lo[3], hi[3];
+    double bmin[3], bmax[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      int c = (int)fmax(-1.0, fmin(floor((tc[d] - b.bbmin[d]) * b.inv_h), (double)b.nc[d]));
+      c = min(max(c, 0), b.nc[d] - 1);
+      lo[d] = __reduce_min_sync(FULL, c);
+      hi[d] = __reduce_max_sync(FULL, c);
+      double mn = tc[d], mx = tc[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(FULL, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+      }
+      bmin[d] = mn;
+      bmax[d] = mx;
+    }
+    int cnt = 0;              // heap fill: the same on every lane (all lanes see the same candidates)
+    double worst = inf;
+    // candidate records are staged through shared memory 32 at a time: one coalesced load per chunk instead of a
+    // dependent global load per candidate
+    double4* stage = reinterpret_cast<double4*>(smem_raw + (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int))) +
+                     (threadIdx.x >> 5) * 32;
+    auto consider = [&](int q, const double d2) {
+      if (cnt < k) {
+        sift_up(hp, cnt, d2, q, sidx);
+        cnt++;
+        if (cnt == k) worst = hp.D(0);
+      } else if (d2 <= worst) {
+        if (key_less(d2, q, hp.D(0), hp.P(0), sidx)) {
+          sift_down(hp, 0, k, d2, q, sidx);
+          worst = hp.D(0);
+        }
+      }
+    };
+    for (int ring = 0; ring <= maxring; ++ring) {
+      double wmax = inf;
+      if (cnt == k) {
+        wmax = worst;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(FULL, wmax, o));
+      }
+      const int zlo = max(lo[2] - ring, 0), zhi = min(hi[2] + ring, b.nc[2] - 1);
+      const int ylo = max(lo[1] - ring, 0), yhi = min(hi[1] + ring, b.nc[1] - 1);
+      const int xlo = max(lo[0] - ring, 0), xhi = min(hi[0] + ring, b.nc[0] - 1);
+      for (int cz = zlo; cz <= zhi; ++cz) {
+        const bool zface = (cz == lo[2] - ring) || (cz == hi[2] + ring);
+        for (int cy = ylo; cy <= yhi; ++cy) {
+          const bool yface = (cy == lo[1] - ring) || (cy == hi[1] + ring);
+          const int rowbase = b.nc[0] * (cy + b.nc[1] * cz);
+          // on a z- or y-face of the shell the whole x-run is new; otherwise only its two end cells
+          int nseg, segx[2][2];
+          if (zface || yface || ring == 0) {
+            nseg = 1;
+            segx[0][0] = xlo;
+            segx[0][1] = xhi;
+          } else {
+            nseg = 0;
+            if (lo[0] - ring >= 0) {
+              segx[nseg][0] = segx[nseg][1] = lo[0] - ring;
+              nseg++;
+            }
+            if (hi[0] + ring <= b.nc[0] - 1) {
+              segx[nseg][0] = segx[nseg][1] = hi[0] + ring;
+              nseg++;
+            }
+          }
+          int clo = 0, chi = b.nc[0] - 1;
+          if (cnt == k) {
+            const double ylo_ = b.bbmin[1] + (double)cy * b.h, zlo_ = b.bbmin[2] + (double)cz * b.h;
+            const double gy = fmax(0.0, fmax(ylo_ - bmax[1], bmin[1] - (ylo_ + b.h))) - 1e-9 * b.h;
+            const double gz = fmax(0.0, fmax(zlo_ - bmax[2], bmin[2] - (zlo_ + b.h))) - 1e-9 * b.h;
+            const double gyz2 = (gy > 0.0 ? gy * gy : 0.0) + (gz > 0.0 ? gz * gz : 0.0);
+            if (gyz2 > wmax) continue;
+            const double w = __dsqrt_ru(wmax - gyz2) * (1.0 + 1e-12) + 1e-9 * b.h;
+            clo = (int)fmax(-1.0, fmin(floor((bmin[0] - w - b.bbmin[0]) * b.inv_h), (double)b.nc[0]));
+            chi = (int)fmax(-1.0, fmin(floor((bmax[0] + w - b.bbmin[0]) * b.inv_h), (double)b.nc[0]));
+          }
+          for (int sgi = 0; sgi < nseg; ++sgi) {
+            const int x0 = max(segx[sgi][0], clo), x1 = min(segx[sgi][1], chi);
+            if (x0 > x1) continue;
+            const int beg = cs[rowbase + x0];
+            const int end = cs[rowbase + x1 + 1];
+            for (int q0 = beg; q0 < end; q0 += 32) {
+              const int nq = min(32, end - q0);
+              __syncwarp();
+              if (lane < nq) stage[lane] = rec[q0 + lane];
+              __syncwarp();
+              int j = 0;
+              for (; j < nq; ++j) {
+                const double4 r = stage[j];
+                consider(q0 + j, gsm_d2_key(r.x, r.y, r.z, tx, ty, tz));
+              }
+            }
+          }
+        }
+      }
+      // per lane: distance from its target to the nearest face of the covered box with unvisited cells behind it
+      double reach = inf;
+      bool any = false;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        if (lo[d] - ring > 0) {
+          reach = fmin(reach, tc[d] - (b.bbmin[d] + (double)(lo[d] - ring) * b.h));
+          any = true;
+        }
+        if (hi[d] + ring < b.nc[d] - 1) {
+          reach = fmin(reach, (b.bbmin[d] + (double)(hi[d] + ring + 1) * b.h) - tc[d]);
+          any = true;
+        }
+      }
+      if (!any) break;  // every cell visited (uniform: lo / hi / ring are)
+      bool done = false;
+      if (cnt == k) {
+        const double safe = reach - 1e-9 * b.h;   // a sample can sit a rounding error outside its nominal cell box
+        done = safe > 0.0 && worst < safe * safe;
+      }
+      if (__all_sync(FULL, done)) break;
+    }
+    if (active) emit(t0, cnt);
+    return;
+  }
 
   for (int run = 0; run < KNN_RUN; ++run) {
     const long long t = t0 + run;
@@ -262,60 +464,7 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
     }
     prev_worst = (cnt == k) ? worst : inf;
 
-    if (idw.on && idw.mode < 0) {
-      // ---- NN model (nn.jl:47-54): the nearest sample's value; among equidistant samples the lowest row ----
-      int best = -1;
-      for (int i = 0; i < cnt; ++i)
-        if (best < 0 || key_less(hp.D(i), hp.P(i), hp.D(best), hp.P(best), sidx)) best = i;
-      idw.mean[t] = best >= 0 ? rec[hp.P(best)].w : __longlong_as_double(0x7ff8000000000000LL);
-      if (idw.status) idw.status[t] = best >= 0 ? GSM_ST_OK : GSM_ST_MISSING;
-      out_cnt[t] = cnt;
-      continue;
-    }
-    if (idw.on) {
-      // ---- fused local IDW over the selected neighbours, in heap order (the order idw_local_kernel would see) ----
-      double sw = 0.0, swz = 0.0, hitv = 0.0;
-      int nkeep = 0, hitrow = 0x7fffffff;
-      for (int i = 0; i < cnt; ++i) {
-        const double d2 = hp.D(i);
-        if (radius > 0.0 && !(__dsqrt_rn(d2) <= radius)) continue;
-        nkeep++;
-        const int q = hp.P(i);
-        const double val = rec[q].w;
-        if (d2 > 0.0) {
-          const double w = gsm_idww::idw_weight_rt(idw.mode, d2, idw.e, idw.ei);
-          sw += w;
-          swz = fma(w, val, swz);
-        } else {   // exact hit: the FIRST such sample of the reference's ascending (d2, row) list = lowest row
-          const int rw = sidx[q];
-          if (rw < hitrow) {
-            hitrow = rw;
-            hitv = val;
-          }
-        }
-      }
-      out_cnt[t] = nkeep;
-      if (nkeep < idw.minn || nkeep <= 0) {
-        idw.mean[t] = __longlong_as_double(0x7ff8000000000000LL);
-        if (idw.status) idw.status[t] = GSM_ST_MISSING;
-      } else {
-        idw.mean[t] = hitrow != 0x7fffffff ? hitv : swz / sw;
-        if (idw.status) idw.status[t] = GSM_ST_OK;
-      }
-      continue;
-    }
-    // ---- emit (heap order); KBallSearch keeps neighbours with distance <= radius (models.jl:158) ----
-    int* o = out_pos + t * (long long)k;
-    int nkeep = 0;
-    if (radius > 0.0) {
-      for (int i = 0; i < cnt; ++i)
-        if (__dsqrt_rn(hp.D(i)) <= radius) o[nkeep++] = hp.P(i);
-    } else {
-      for (int i = 0; i < cnt; ++i) o[i] = hp.P(i);
-      nkeep = cnt;
-    }
-    for (int i = nkeep; i < k; ++i) o[i] = -1;
-    out_cnt[t] = nkeep;
+    emit(t, cnt);
   }
 }
 
@@ -361,7 +510,7 @@ __global__ void pos_to_rows_kernel(const int* __restrict__ pos, long long total,
 static int launch_knn_impl(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, const KnnIdw& idw, int* d_pos,
                            int* d_cnt) {
   if (tg.count <= 0) return GSM_OK;
-  size_t smem = (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int));
+  size_t smem = (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int)) + (KNN_THREADS / 32) * 32 * sizeof(double4);
   GSM_CUDA(ctx, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long blocks = (tg.count + (long long)KNN_THREADS * KNN_RUN - 1) / ((long long)KNN_THREADS * KNN_RUN);
   int tiled = 0, ntx = 1;
