@@ -270,7 +270,7 @@ def test_error_codes(gsm):
     assert e.value.code == L.GSM_ERR_NO_SAMPLES
     c.set_samples(np.random.default_rng(0).uniform(size=(100, 2)), np.zeros(100))
     with pytest.raises(gsm.GsmError) as e:
-        c.local_krige(L.make_variogram(7, 1, 0, 1), L.make_model(L.GSM_KRIG_ORDINARY), t, 8)
+        c.local_krige(L.make_variogram(9, 1, 0, 1), L.make_model(L.GSM_KRIG_ORDINARY), t, 8)
     assert e.value.code == L.GSM_ERR_INVALID
     with pytest.raises(gsm.GsmError) as e:
         c.local_krige(L.make_variogram(1, 1, 0, 1), L.make_model(L.GSM_KRIG_ORDINARY),
@@ -528,7 +528,7 @@ STEADY = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["auto", "patch", "shr", "pipe"])
+@pytest.mark.parametrize("impl", ["auto", "patch", "pipe"])
 @pytest.mark.parametrize("kind,dim,deg,k,dims,n,first,count,nbh", STEADY)
 def test_shared_factor_kernel_steady_state(gsm, oracle, kind, dim, deg, k, dims, n, first, count, nbh, impl):
     """Grids large enough that every CTA of the persistent kernels runs many jobs (the 3-stage shared-factor
@@ -757,7 +757,7 @@ def test_c2_class_gaussian_local_against_exact_arithmetic(gsm, oracle):
 
 
 def test_randomised_parity_sweep(gsm, oracle):
-    """120 random neighbourhood cases (model, variogram, dimension, k up to 64, grid shape, slab, radius,
+    """90 random neighbourhood cases (model, variogram, dimension, k up to 64, grid shape, slab, radius,
     minneighbors, coincident samples) against the C oracle: tools/fuzz_parity.py."""
     import importlib.util, os
     spec = importlib.util.spec_from_file_location(
@@ -765,7 +765,7 @@ def test_randomised_parity_sweep(gsm, oracle):
     fz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fz)
     bad = []
-    for seed in range(5000, 5120):
+    for seed in range(5000, 5090):
         ok, desc = fz.one(seed)
         if not ok:
             bad.append(desc)
