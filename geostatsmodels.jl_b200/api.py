@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 
 __all__ = [
-    "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "CubicVariogram", "PentasphericalVariogram",
+    "CoregionalizedVariogram", "GaussianVariogram", "SphericalVariogram", "ExponentialVariogram", "CubicVariogram", "PentasphericalVariogram",
     "SineHoleVariogram", "CircularVariogram", "NuggetEffect", "CompositeVariogram", "PointSet", "CartesianGrid", "GeoTable",
     "georef", "IDW", "NN", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
     "predict", "predictprob", "status", "fitpredict", "default_context", "multi_context", "set_default_device", "Dirac",
@@ -119,6 +119,36 @@ class CompositeVariogram:
 
     def __rmul__(self, c):
         return CompositeVariogram([(float(c) * a, f) for a, f in self.terms])
+
+
+class CoregionalizedVariogram:
+    """B * gamma0: a matrix coefficient times a scalar variogram (GeoStatsFunctions: `[1.0 0.3; 0.3 1.0] * gamma`), the
+    multivariate function of the reference's CoKriging tests (test/krig.jl:348-395).  With every variable observed at
+    every sample the cokriging system (C0 (x) B) decouples: the weights of every variable are the scalar Kriging
+    weights of gamma0 and the covariance of the prediction is B times the scalar variance ("autokrigeability" of the
+    proportional model; tests/test_cokriging.py checks it against the reference's full (nobs nvar + ncon nvar) system
+    restated in oracle/).  The GPU path therefore serves this form with one univariate solve per variable."""
+
+    def __init__(self, B, base):
+        self.B = np.asarray(B, dtype=np.float64)
+        if self.B.ndim != 2 or self.B.shape[0] != self.B.shape[1] or not np.allclose(self.B, self.B.T):
+            raise ValueError("the coefficient must be a symmetric matrix")
+        self.base = base
+
+    @property
+    def nvariables(self):
+        return self.B.shape[0]
+
+    @property
+    def range(self):
+        return self.base.range
+
+    def scaled(self, alpha):
+        return CoregionalizedVariogram(self.B, self.base.scaled(alpha))
+
+    def marginal(self, p):
+        """the variogram of variable p alone: B[p, p] * gamma0"""
+        return float(self.B[p, p]) * self.base
 
 
 class GaussianVariogram(_Variogram):
@@ -402,10 +432,25 @@ def _single_column(data: GeoTable):
     return names
 
 
+def _nvariables(model) -> int:
+    return getattr(getattr(model, "fun", None), "nvariables", 1)
+
+
 def _checkcompat(model, data: GeoTable):  # krig.jl:78-85
     nfeat = len(data.names())
-    if isinstance(model, _KrigingModel) and nfeat != 1:
-        raise ValueError(f"{nfeat} data column(s) provided to 1-variate Kriging model")
+    nvar = _nvariables(model)
+    if isinstance(model, _KrigingModel) and nfeat != nvar:
+        raise ValueError(f"{nfeat} data column(s) provided to {nvar}-variate Kriging model")
+
+
+def _marginal_model(model, p):
+    """the univariate model of variable p of a cokriging model with a proportional covariance"""
+    f = model.fun.marginal(p)
+    if isinstance(model, SimpleKriging):
+        return SimpleKriging(f, float(np.atleast_1d(model.mean)[p]))
+    if isinstance(model, OrdinaryKriging):
+        return OrdinaryKriging(f)
+    return UniversalKriging(f, exps=model.exps)
 
 
 def _pointset_of(domain) -> np.ndarray:
@@ -579,6 +624,23 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         raise NotImplementedError("only the Euclidean distance is claimed by the GPU path")
     if not isinstance(dom, (PointSet, CartesianGrid)):
         dom = PointSet(dom)
+    if _nvariables(model) > 1:
+        # CoKriging with a proportional covariance B * gamma0 and isotopic data: one univariate solve per variable
+        _checkcompat(model, data)
+        cols = {}
+        for p_, name in enumerate(data.names()):
+            if np.isnan(_values_of(data, name)).any():
+                raise NotImplementedError("cokriging with missing values (heterotopic data) is not claimed by the GPU path")
+            one = fitpredict(_marginal_model(model, p_), GeoTable({name: data.table[name]}, data.domain), dom, point=point,
+                             prob=prob, neighbors=neighbors, minneighbors=minneighbors, maxneighbors=maxneighbors,
+                             neighborhood=neighborhood, distance=distance, device=device, devices=devices, first=first,
+                             count=count, ctx=ctx)
+            cols[name] = one.table[name]
+        pred = GeoTable.__new__(GeoTable)
+        pred.table = cols
+        pred.domain = dom
+        pred.shard = one.shard
+        return pred
     if _device_samples is not None:
         # (distributed.fitpredict_sharded) the samples already sit in device memory on this rank: an NCCL broadcast
         # delivered them; `data` only carries the column name

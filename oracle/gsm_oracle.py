@@ -310,6 +310,70 @@ class KrigingSystem:
         return mu, var
 
 
+class CoKrigingSystem:
+    """FittedKriging for a multivariate function of the proportional form  B * gamma0  (a matrix coefficient times a
+    scalar variogram: `[1.0 0.3; 0.3 1.0] * SphericalVariogram(range=35.0)`, test/krig.jl:348-395), restated from the
+    reference with nvar > 1: interleaved unknowns (sample-major, variable-minor), LHS[i, j] = S[mod1(i, nvar),
+    mod1(j, nvar)] - gamma (krig.jl:165-179), one constraint per variable and drift (ordinary.jl:33-58,
+    universal.jl:81-113), an nfun x nvar right-hand side (krig.jl:342-378; ordinary.jl:60-77; universal.jl:115-137),
+    krigmean (krig.jl:245-258 / simple.jl:55-69) and the covariance formula (krig.jl:264-313)."""
+
+    def __init__(self, kind: int, B: np.ndarray, vario: Variogram, X: np.ndarray, Z: np.ndarray, mean=None, exps=()):
+        self.kind, self.vario = kind, vario
+        self.B = np.asarray(B, dtype=np.float64)
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.Z = np.asarray(Z, dtype=np.float64)          # nobs x nvar
+        self.mean = None if mean is None else np.asarray(mean, dtype=np.float64)
+        self.exps = tuple(exps)
+        nv = self.B.shape[0]
+        n = self.X.shape[0]
+        nd = {SK: 0, OK: 1}.get(kind, len(self.exps))
+        self.nv, self.n, self.nfun, self.ncon = nv, n, n * nv, nd * nv
+        m = self.nfun + self.ncon
+        G = variogram(vario, pairdist(self.X, self.X))    # scalar gamma0 between the samples
+        S = self.B * vario.total_sill                      # sill(fun): the matrix of sills
+        LHS = np.zeros((m, m), order="F")
+        LHS[:self.nfun, :self.nfun] = np.kron(np.ones((n, n)), S) - np.kron(G, self.B)
+        F = np.ones((n, 1)) if kind == OK else (drift_matrix(self.exps, self.X) if kind == UK else np.zeros((n, 0)))
+        for q in range(F.shape[1]):
+            for e in range(n):
+                for v in range(nv):
+                    LHS[self.nfun + q * nv + v, e * nv + v] = F[e, q]
+                    LHS[e * nv + v, self.nfun + q * nv + v] = F[e, q]
+        self.LHS = LHS
+        self._ldu, self._ipiv, self.info = lapack.dsytrf(LHS, lower=0)
+
+    def predict(self, x0):
+        """(means[nvar], variances[nvar]) at x0: diag of Sigma + 1e-10 I as `var(MvNormal)` sees it"""
+        x0 = np.asarray(x0, dtype=np.float64)
+        nv, n = self.nv, self.n
+        g = variogram(self.vario, pairdist(self.X, x0[None, :])[:, 0])
+        S = self.B * self.vario.total_sill
+        R = np.zeros((self.nfun + self.ncon, nv))
+        for e in range(n):
+            R[e * nv:(e + 1) * nv, :] = S - g[e] * self.B
+        if self.kind == OK:
+            f0 = np.ones(1)
+        elif self.kind == UK:
+            f0 = drift_matrix(self.exps, x0[None, :])[0]
+        else:
+            f0 = np.zeros(0)
+        for q in range(len(f0)):
+            for v in range(nv):
+                R[self.nfun + q * nv + v, v] = f0[q]
+        W, info = lapack.dsytrs(self._ldu, self._ipiv, R, lower=0)
+        lam, nu = W[:self.nfun], W[self.nfun:]
+        mu = np.zeros(nv)
+        for j in range(nv):
+            acc = 0.0
+            for p_ in range(nv):
+                zp = self.Z[:, p_] - (self.mean[p_] if self.kind == SK else 0.0)
+                acc += float(np.sum(lam[p_::nv, j] * zp))
+            mu[j] = acc + (self.mean[j] if self.kind == SK else 0.0)
+        Sigma = S - R[:self.nfun].T @ lam - R[self.nfun:].T @ nu + VAR_EPS * np.eye(nv)
+        return mu, np.diag(Sigma).copy()
+
+
 # ----------------------------------------------------------------------------------------------
 # Domains, scaling (models.jl:265-296)
 # ----------------------------------------------------------------------------------------------
