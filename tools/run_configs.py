@@ -10,6 +10,7 @@ import __graft_entry__ as entry
 ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--only", default="")
+ap.add_argument("--gpus", type=int, default=1)
 args = ap.parse_args()
 gsm = entry.load_package()
 o = entry.load_oracle()
@@ -125,22 +126,43 @@ def ns():
 
 
 def c5():
+    """C5: SimpleKriging + IDW sweep, samples 10^4 .. 10^7, k = 8 .. 64, 2-D (2048^2) and 3-D (256^3) grids, random and
+    LATTICE samples (integer lattice: distance ties everywhere), on --gpus GPUs through fitpredict(devices=...)."""
     out = {}
+    devs = list(range(args.gpus)) if args.gpus > 1 else None
+    tctx = None if devs else ctx
+    def tim():
+        if devs:
+            mc = gsm.multi_context(devs)
+            t = [mc.device_timings(i) for i in range(len(devs))]
+            return {"knn_ms": max(x["knn_ms"] for x in t), "solve_ms": max(x["solve_ms"] for x in t)}
+        return ctx.timings()
     for dim, dims in ((2, (2048 // Q, 2048 // Q)), (3, (256 // Q,) * 3)):
-        for n in (10_000, 1_000_000 // (Q if dim == 2 else 1)):
-            rng = np.random.default_rng(5)
-            X = rng.uniform(0, dims[0], size=(n, dim)); z = rng.standard_normal(n)
-            tab = gsm.georef({"z": z}, gsm.PointSet(X)); grid = gsm.CartesianGrid(*dims)
-            for k in (8, 16, 32, 64):
-                sk = gsm.SimpleKriging(gsm.SphericalVariogram(range=dims[0] / 20, nugget=0.1), float(z.mean()))
-                _, dt = timed(lambda: gsm.fitpredict(sk, tab, grid, maxneighbors=k, prob=True, ctx=ctx), reps=1)
-                t = ctx.timings()
-                out[f"SK {dim}D N={n} k={k}"] = {"e2e_ms": round(dt * 1e3, 1), "knn_ms": round(t["knn_ms"], 2), "solve_ms": round(t["solve_ms"], 2)}
-            for k in (8, 32, 64):
-                _, dt = timed(lambda: gsm.fitpredict(gsm.IDW(2), tab, grid, maxneighbors=k, ctx=ctx), reps=1)
-                t = ctx.timings()
-                out[f"IDW {dim}D N={n} k={k}"] = {"e2e_ms": round(dt * 1e3, 1), "knn_ms": round(t["knn_ms"], 2), "solve_ms": round(t["solve_ms"], 2)}
-    return {"M2d": (2048 // Q) ** 2, "M3d": (256 // Q) ** 3, "results": out}
+        for n in (10_000, 100_000, 1_000_000, 10_000_000):
+            if args.quick and n > 1_000_000:
+                continue
+            for lattice in (False, True):
+                if lattice and n != 1_000_000:
+                    continue
+                rng = np.random.default_rng(5)
+                X = rng.uniform(0, dims[0], size=(n, dim))
+                if lattice:   # samples on a lattice of pitch ~ (volume / n)^(1/dim): every distance is tied many times
+                    pitch = dims[0] / round(n ** (1.0 / dim))
+                    X = (np.floor(X / pitch) + 0.5) * pitch
+                    X = np.unique(X, axis=0)
+                z = rng.standard_normal(X.shape[0])
+                tab = gsm.georef({"z": z}, gsm.PointSet(X)); grid = gsm.CartesianGrid(*dims)
+                tag = f"{dim}D N={X.shape[0]}{' lattice' if lattice else ''}"
+                for k in (8, 16, 32, 64):
+                    sk = gsm.SimpleKriging(gsm.SphericalVariogram(range=dims[0] / 20, nugget=0.1), float(z.mean()))
+                    _, dt = timed(lambda: gsm.fitpredict(sk, tab, grid, maxneighbors=k, prob=True, ctx=tctx, devices=devs), reps=1)
+                    t = tim()
+                    out[f"SK {tag} k={k}"] = {"e2e_ms": round(dt * 1e3, 1), "knn_ms": round(t["knn_ms"], 2), "solve_ms": round(t["solve_ms"], 2)}
+                for k in (8, 32, 64):
+                    _, dt = timed(lambda: gsm.fitpredict(gsm.IDW(2), tab, grid, maxneighbors=k, ctx=tctx, devices=devs), reps=1)
+                    t = tim()
+                    out[f"IDW {tag} k={k}"] = {"e2e_ms": round(dt * 1e3, 1), "knn_ms": round(t["knn_ms"], 2), "solve_ms": round(t["solve_ms"], 2)}
+    return {"gpus": args.gpus, "M2d": (2048 // Q) ** 2, "M3d": (256 // Q) ** 3, "results": out}
 
 
 for name, fn in (("C1 IDW global", c1), ("C2 OK Gaussian global", c2), ("C3 local OK k=32", c3), ("C4 UK quadratic 3D", c4), ("NS OK 3D 1M->256^3", ns), ("C5 sweep", c5)):
