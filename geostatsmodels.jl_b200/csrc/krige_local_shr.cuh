@@ -55,7 +55,8 @@ constexpr int PMAX = GSM_JOB_PMAX;         // pool capacity (distinct samples pe
 constexpr int PLD = PMAX + 1;              // leading dimension of the pooled matrix (odd: spreads banks)
 constexpr int NBJ = 4;                     // pool / shared-factor buffers (pools are loaded 4 jobs ahead)
 constexpr int NBH = 8;                     // job descriptors in shared memory (loaded 5 jobs ahead)
-constexpr int BAR_READY = 1, BAR_DONE = 2, BAR_POOL = 3, BAR_EPI = 4, BAR_START = 5;
+constexpr int BAR_READY = 1, BAR_DONE = 2, BAR_POOL = 3, BAR_EPI = 4, BAR_START = 5, BAR_FREE0 = 6;   // (+ BAR_FREE0 + 1)
+constexpr int WE = SW + 1;                 // epilogue warp (only with many drift functions, see EPIW below)
 
 __device__ __forceinline__ void dmma(double2& d, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -209,12 +210,15 @@ struct alignas(128) ShrSmem {
   double fW[NBJ][3][64];                                // inverse diagonal factors of the shared columns
   double fL[NBJ][3][64];                                // shared blocks (1,0), (2,0), (2,1)
   int hbad[NBH][4];                                     // shared diagonal block not positive definite
-  int flag[2][SW];                                      // private diagonal-block failures, by job parity
+  int flag[4][SW];                                      // private diagonal-block failures, by job mod 4
 };
 
 // NCON: constraints (drift monomials); NBC: 8-wide block columns of the covariance block (k <= 8 NBC)
+// EPIW (more than 6 drift functions, i.e. two right-hand-side block rows): the thread-per-system epilogue -- a fully
+// unrolled Cholesky of the NCON x NCON drift Schur complement, ~2000 instructions for 10 drifts -- runs in a TENTH
+// warp instead of the diagonal-block warp, whose hand-off rounds are on every system warp's critical path.
 template <int NCON, bool DIM3, int NBC>
-__global__ void __launch_bounds__(NTH, (2 + NCON > 8) ? 1 : 2)
+__global__ void __launch_bounds__(NTH + ((2 + NCON > 8) ? 32 : 0), (2 + NCON > 8) ? 1 : 2)
 local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant__ VarioDev v,
                        const __grid_constant__ ModelDev m, const __grid_constant__ TargetsDev tg,
                        const __grid_constant__ CovFast cf, const JobIdx* __restrict__ jobs, long long ngroups, int k,
@@ -223,6 +227,8 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
                        unsigned char* __restrict__ out_status) {
   constexpr int NR = 2 + NCON;
   constexpr int NRB = NR > 8 ? 2 : 1;       // right-hand-side block rows
+  constexpr bool EPIW = NR > 8;             // epilogue in its own warp
+  constexpr int NTHK = NTH + (EPIW ? 32 : 0);
   constexpr int NGB = NRB * (NRB + 1) / 2;
   constexpr int NROWS = NBC + NRB;          // block rows of the augmented matrix
   constexpr int KMAX = 8 * NBC;             // neighbour slots
@@ -239,8 +245,8 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
   // jobs of this CTA: patches blockIdx.x, blockIdx.x + gridDim.x, ...
   const int niter = (int)((ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  for (int e = threadIdx.x; e < SW * EXS; e += NTH) S.exout[e] = 0.0;
-  for (int e = threadIdx.x; e < NBH * 4; e += NTH) (&S.hbad[0][0])[e] = 0;
+  for (int e = threadIdx.x; e < SW * EXS; e += NTHK) S.exout[e] = 0.0;
+  for (int e = threadIdx.x; e < NBH * 4; e += NTHK) (&S.hbad[0][0])[e] = 0;
   __syncthreads();
 
   // (cf: the covariance constants, a kernel parameter so they are constant-bank operands, not 20 live registers)
@@ -286,8 +292,8 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
     }
   };
 
-  if (warp == WD) {
-    // ---------------- diagonal-block warp ----------------
+  if (warp == WD || (EPIW && warp == WE)) {
+    // ---------------- diagonal-block warp (and, with EPIW, the epilogue warp) ----------------
     // one hand-off round: lanes 0..7 private blocks (when `priv`), lanes 8..10 the shared stages (when `shared`)
     auto round = [&](int j, bool priv, bool shared) __attribute__((always_inline)) {
       const double* in = nullptr;
@@ -297,7 +303,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         if (priv) {
           in = &S.exin[lane * EXS];
           out = &S.exout[lane * EXS];
-          badp = &S.flag[j & 1][lane];
+          badp = &S.flag[j & 3][lane];
         }
       } else if (lane < SW + 3 && shared && SMAX >= 1) {
         const int s = lane - SW, q = j + 3 - s;
@@ -322,7 +328,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
           return Gj[(lane * NGB + br * (br + 1) / 2 + bc) * EXS + (a & 7) * 8 + (bb & 7)];
         };
         const long long tt = Jj.tt[lane];
-        bool singular = S.flag[j & 1][lane] != 0 || (S.hbad[jh][0] | S.hbad[jh][1] | S.hbad[jh][2]) != 0;
+        bool singular = S.flag[j & 3][lane] != 0 || (S.hbad[jh][0] | S.hbad[jh][1] | S.hbad[jh][2]) != 0;
         const double uu = -Gm(0, 0), wu = -Gm(1, 0);
         const double c0 = v.sill;
         double mean, var;
@@ -402,6 +408,16 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       }
     };
 
+    if (EPIW && warp == WE) {
+      // epilogue warp: job ji's Schur blocks arrive with BAR_EPI; the system warps may refill that Gx buffer (job
+      // ji + 2) only after BAR_FREE0 + (ji & 1)
+      for (int ji = 0; ji < niter; ++ji) {
+        bar_sync(BAR_EPI, NSD);
+        epilogue(ji);
+        bar_arrive(BAR_FREE0 + (ji & 1), NSYS + 32);
+      }
+      return;
+    }
     // prologue: start the shared-factor pipeline (virtual jobs -4..-1: the system warps prepare, this warp factors)
     for (int jv = -5; jv < 0; ++jv) {
       bar_sync(BAR_START, NTH);
@@ -410,21 +426,23 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       bar_sync(BAR_START, NTH);
     }
     for (int ji = 0; ji < niter; ++ji) {
-      if (ji >= 1) bar_sync(BAR_EPI, NSD);   // Schur blocks of job ji-1 are in
+      if (!EPIW && ji >= 1) bar_sync(BAR_EPI, NSD);   // Schur blocks of job ji-1 are in
       const int S_ = S.J[ji & (NBH - 1)].S;
-      if (lane < SW) S.flag[ji & 1][lane] = 0;
+      if (lane < SW) S.flag[ji & 3][lane] = 0;
       for (int r = 0; r < NBC - S_; ++r) {
         bar_sync(BAR_READY, NSD);
         if (r == 0) TR(0);
         round(ji, true, r == 0);
         bar_arrive(BAR_DONE, NSD);
         if (r == 0) TR(1);
-        if (r == 0 && ji >= 1) epilogue(ji - 1);   // previous job (its Schur blocks are double-buffered)
+        if (!EPIW && r == 0 && ji >= 1) epilogue(ji - 1);   // previous job (its Schur blocks are double-buffered)
         if (r == 0) TR(2);
       }
     }
-    bar_sync(BAR_EPI, NSD);
-    epilogue(niter - 1);
+    if (!EPIW) {
+      bar_sync(BAR_EPI, NSD);
+      epilogue(niter - 1);
+    }
     return;
   }
 
@@ -781,6 +799,7 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         for (int kb = KREL + 1; kb < NBC; ++kb) column(kb, std::false_type{}, SAny{});
       }
       // ---- hand the trailing Schur blocks (-B'C^-1B) to the diagonal warp for the epilogue --------
+      if (EPIW && ji >= 2) bar_sync(BAR_FREE0 + (ji & 1), NSYS + 32);   // the epilogue warp is done with this buffer
 #pragma unroll
       for (int r = 0; r < NRB; ++r)
 #pragma unroll
@@ -811,7 +830,7 @@ int launch_shr(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const Targets
   const int blocks = (int)std::min<long long>(ngroups, 148LL * per_sm);
   auto kern = local_krige_shr_kernel<NCON, DIM3, NBC>;
   GSM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, NTH, smem, ctx->stream>>>(ctx->bins, v, m, tg, make_cov(v), jobs, ngroups, k, centered, pos, mean, var,
+  kern<<<blocks, NTH + ((2 + NCON > 8) ? 32 : 0), smem, ctx->stream>>>(ctx->bins, v, m, tg, make_cov(v), jobs, ngroups, k, centered, pos, mean, var,
                                            status);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
