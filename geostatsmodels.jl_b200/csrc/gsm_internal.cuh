@@ -331,9 +331,13 @@ __device__ __forceinline__ double gsm_cov_vec(const VarioDev& v, double dx, doub
   return gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
 }
 
+// x^p by repeated multiplication (universal.jl:60-62: `x .^ n` with integer n), same rounding as the plain loop
+// r = 1; r *= x (p times); exponents 0..2 (every drift up to quadratic) take no loop
 __device__ __forceinline__ double gsm_ipow(double x, int p) {
-  double r = 1.0;
-  for (int i = 0; i < p; ++i) r *= x;
+  if (p <= 0) return 1.0;
+  if (p == 1) return x;
+  double r = x * x;
+  for (int i = 2; i < p; ++i) r *= x;
   return r;
 }
 
