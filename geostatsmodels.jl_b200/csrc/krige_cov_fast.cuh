@@ -36,7 +36,7 @@ __host__ __device__ __forceinline__ CovFast make_cov(const VarioDev& v) {
 __device__ __forceinline__ double cov_fast(const CovFast& c, double d2) {
   if (c.kind == GSM_VARIO_SPHERICAL) {
     const double t2 = d2 * c.inv_r2;
-    const double y = fast_rsqrt(fmax(d2, 1e-300));
+    const double y = fast_rsqrt(__hiloint2double(max(__double2hiint(d2), 0x03e00000), __double2loint(d2)));
     const double t = (d2 * c.inv_r) * y;
     double v = fma(t, fma(c.k2, t2, c.k1), c.c1);
     v = (d2 < c.range2) ? v : c.cfar;
@@ -46,7 +46,7 @@ __device__ __forceinline__ double cov_fast(const CovFast& c, double d2) {
     const double v = c.sill - (c.cs * (1.0 - exp(-3.0 * t2)) + (c.sill - c.c1));
     return (d2 > 0.0) ? v : c.sill;
   } else {
-    const double y = fast_rsqrt(fmax(d2, 1e-300));
+    const double y = fast_rsqrt(__hiloint2double(max(__double2hiint(d2), 0x03e00000), __double2loint(d2)));
     const double t = (d2 * c.inv_r) * y;
     const double v = c.sill - (c.cs * (1.0 - exp(-3.0 * t)) + (c.sill - c.c1));
     return (d2 > 0.0) ? v : c.sill;

@@ -96,10 +96,35 @@ __host__ __device__ __forceinline__ CovFast make_cov(const VarioDev& v) {
   c.cfar = v.sill - (v.cs + v.nadd);
   return c;
 }
+// d2 >= 0 clamped to >= ~1e-290 with ONE integer max on the high word (fmax on doubles is ~8 instructions); keeps
+// 1/sqrt finite for an exact hit, whose covariance the final select replaces by the sill anyway
+__device__ __forceinline__ double clamp_d2(double d2) {
+  return __hiloint2double(max(__double2hiint(d2), 0x03e00000), __double2loint(d2));
+}
+// the same with the variogram kind as a compile-time constant (no branch per evaluation)
+template <int KIND>
+__device__ __forceinline__ double cov_kind(const CovFast& c, double d2) {
+  double v;
+  if (KIND == GSM_VARIO_SPHERICAL) {
+    const double t2 = d2 * c.inv_r2;
+    const double y = fast_rsqrt(clamp_d2(d2));
+    const double t = (d2 * c.inv_r) * y;
+    v = fma(t, fma(c.k2, t2, c.k1), c.c1);
+    v = (d2 < c.range2) ? v : c.cfar;
+  } else if (KIND == GSM_VARIO_GAUSSIAN) {
+    const double t2 = d2 * c.inv_r2;
+    v = c.sill - (c.cs * (1.0 - exp(-3.0 * t2)) + (c.sill - c.c1));
+  } else {
+    const double y = fast_rsqrt(clamp_d2(d2));
+    const double t = (d2 * c.inv_r) * y;
+    v = c.sill - (c.cs * (1.0 - exp(-3.0 * t)) + (c.sill - c.c1));
+  }
+  return (d2 > 0.0) ? v : c.sill;
+}
 __device__ __forceinline__ double cov_fast(const CovFast& c, double d2) {
   if (c.kind == GSM_VARIO_SPHERICAL) {
     const double t2 = d2 * c.inv_r2;
-    const double y = fast_rsqrt(fmax(d2, 1e-300));
+    const double y = fast_rsqrt(clamp_d2(d2));
     const double t = (d2 * c.inv_r) * y;
     double v = fma(t, fma(c.k2, t2, c.k1), c.c1);
     v = (d2 < c.range2) ? v : c.cfar;
@@ -109,7 +134,7 @@ __device__ __forceinline__ double cov_fast(const CovFast& c, double d2) {
     const double v = c.sill - (c.cs * (1.0 - exp(-3.0 * t2)) + (c.sill - c.c1));
     return (d2 > 0.0) ? v : c.sill;
   } else {
-    const double y = fast_rsqrt(fmax(d2, 1e-300));
+    const double y = fast_rsqrt(clamp_d2(d2));
     const double t = (d2 * c.inv_r) * y;
     const double v = c.sill - (c.cs * (1.0 - exp(-3.0 * t)) + (c.sill - c.c1));
     return (d2 > 0.0) ? v : c.sill;
@@ -547,45 +572,58 @@ local_krige_shr_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
       // exploiting the symmetry costs more index arithmetic than it saves here (measured)
       const int total = (P - S8) * P;    // (negative for overflow jobs: nothing to do)
       const float invP = 1.0f / (float)max(P, 1);
+      auto rows = [&](auto kind_tag) __attribute__((always_inline)) {
+        constexpr int KIND = decltype(kind_tag)::value;     // (the variogram kind is compiled in)
 #pragma unroll 1
-      for (int e = warp * 32 + lane; e < total; e += NSYS) {
-        const int rr = (int)(((float)e + 0.5f) * invP);
-        const int bc = e - rr * P;
-        const int a = S8 + rr;
-        double val = v.sill;
-        if (a != bc) {
-          const double2 axy = *reinterpret_cast<const double2*>(&pr[a]);
-          const double2 bxy = *reinterpret_cast<const double2*>(&pr[bc]);
-          const double dx = axy.x - bxy.x, dy = axy.y - bxy.y;
-          val = cov_fast(cf, fma(dy, dy, dx * dx));
+        for (int e = warp * 32 + lane; e < total; e += NSYS) {
+          const int rr = (int)(((float)e + 0.5f) * invP);
+          const int bc = e - rr * P;
+          const int a = S8 + rr;
+          double val = v.sill;
+          if (a != bc) {
+            const double2 axy = *reinterpret_cast<const double2*>(&pr[a]);
+            const double2 bxy = *reinterpret_cast<const double2*>(&pr[bc]);
+            const double dx = axy.x - bxy.x, dy = axy.y - bxy.y;
+            val = cov_kind<KIND>(cf, fma(dy, dy, dx * dx));
+          }
+          S.PC[a * PLD + bc] = val;
         }
-        S.PC[a * PLD + bc] = val;
-      }
+      };
+      if (cf.kind == GSM_VARIO_SPHERICAL) rows(std::integral_constant<int, GSM_VARIO_SPHERICAL>{});
+      else if (cf.kind == GSM_VARIO_GAUSSIAN) rows(std::integral_constant<int, GSM_VARIO_GAUSSIAN>{});
+      else rows(std::integral_constant<int, GSM_VARIO_EXPONENTIAL>{});
     } else {
       // 3-D patches share less (P - S8 ~ 32 rows): columns b <= a only, the rest by symmetry.  Row a' = a - S8 has
       // S8 + a' + 1 entries; pairing row a' with row Pp-1-a' gives rows of constant width W, so (a, b) follows
-      // from one float multiply.
+      // from one float multiply.  (Round 2 tried rows interleaved over the warps with a plain column loop: a third of
+      // the index arithmetic but unbalanced, 47.4 -> 48.4 ms on the north-star config.)  The variogram kind is compiled in.
       const int Pp = P - S8, W = 2 * S8 + Pp + 1, total = ((Pp + 1) >> 1) * W;
       const float invW = 1.0f / (float)W;
+      auto rows = [&](auto kind_tag) __attribute__((always_inline)) {
+        constexpr int KIND = decltype(kind_tag)::value;
 #pragma unroll 1
-      for (int e = warp * 32 + lane; e < total; e += NSYS) {
-        const int rr = (int)(((float)e + 0.5f) * invW);
-        const int cc = e - rr * W;
-        const bool first = cc <= S8 + rr;
-        const int ap = first ? rr : Pp - 1 - rr;
-        const int bc = first ? cc : cc - (S8 + rr + 1);
-        if (!first && ap == rr) continue;   // odd Pp: the middle row is its own partner
-        const int a = S8 + ap;
-        double val = v.sill;
-        if (a != bc) {
-          const double2 axy = *reinterpret_cast<const double2*>(&pr[a]);
-          const double2 bxy = *reinterpret_cast<const double2*>(&pr[bc]);
-          const double dx = axy.x - bxy.x, dy = axy.y - bxy.y, dz = pr[a].z - pr[bc].z;
-          val = cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+        for (int e = warp * 32 + lane; e < total; e += NSYS) {
+          const int rr = (int)(((float)e + 0.5f) * invW);
+          const int cc = e - rr * W;
+          const bool first = cc <= S8 + rr;
+          const int ap = first ? rr : Pp - 1 - rr;
+          const int bc = first ? cc : cc - (S8 + rr + 1);
+          if (!first && ap == rr) continue;   // odd Pp: the middle row is its own partner
+          const int a = S8 + ap;
+          double val = v.sill;
+          if (a != bc) {
+            const double2 axy = *reinterpret_cast<const double2*>(&pr[a]);
+            const double2 bxy = *reinterpret_cast<const double2*>(&pr[bc]);
+            const double dx = axy.x - bxy.x, dy = axy.y - bxy.y, dz = pr[a].z - pr[bc].z;
+            val = cov_kind<KIND>(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+          }
+          S.PC[a * PLD + bc] = val;
+          if (bc >= S8) S.PC[bc * PLD + a] = val;
         }
-        S.PC[a * PLD + bc] = val;
-        if (bc >= S8) S.PC[bc * PLD + a] = val;
-      }
+      };
+      if (cf.kind == GSM_VARIO_SPHERICAL) rows(std::integral_constant<int, GSM_VARIO_SPHERICAL>{});
+      else if (cf.kind == GSM_VARIO_GAUSSIAN) rows(std::integral_constant<int, GSM_VARIO_GAUSSIAN>{});
+      else rows(std::integral_constant<int, GSM_VARIO_EXPONENTIAL>{});
     }
   };
   // Shared-factor pipeline, system-warp side, run after the last round of job j:
