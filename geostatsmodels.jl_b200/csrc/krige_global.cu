@@ -489,6 +489,16 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
     rc = (expr);                       \
     if (rc != GSM_OK) return fail(rc); \
   } while (0)
+// a CUDA call inside the fit: on failure record the message and leave through fail() (frees the fit's buffers and
+// events, restores the device) instead of GSM_CUDA's bare return
+#define FIT_CUDA(call)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      gsm_set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(e_) + " (global Kriging fit)"); \
+      return fail(GSM_ERR_CUDA);                                                                        \
+    }                                                                                                   \
+  } while (0)
   FIT_TRY(gsm_reserve(ctx, b.C, (size_t)np * np * sizeof(double)));
   FIT_TRY(gsm_reserve(ctx, f->Linv, (size_t)np * np * sizeof(double)));
   FIT_TRY(gsm_reserve(ctx, f->W, (size_t)np * NB * sizeof(double)));        // D = C^-1 [z | F]
@@ -531,7 +541,7 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
       // panel: L_ik = A_ik * inv(L_kk)'   (T is scratch because the GEMM is not in-place safe)
       double* Aik = C + (size_t)kb * NB * np + (kb + 1) * NB;
       FIT_TRY(gemm(ctx, true, rows, NB, NB, 1.0, Aik, np, Dk, NB, 0.0, T, np, 0));
-      GSM_CUDA(ctx, cudaMemcpy2DAsync(Aik, (size_t)np * sizeof(double), T, (size_t)np * sizeof(double),
+      FIT_CUDA(cudaMemcpy2DAsync(Aik, (size_t)np * sizeof(double), T, (size_t)np * sizeof(double),
                                       (size_t)rows * sizeof(double), NB, cudaMemcpyDeviceToDevice, st));
       // trailing update: A_ij -= L_ik L_jk'   (lower tiles only)
       double* Atr = C + (size_t)(kb + 1) * NB * np + (kb + 1) * NB;
@@ -539,7 +549,7 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
     }
   }
   // ---- Linv = L^-1 : blocked forward substitution on the identity ----
-  GSM_CUDA(ctx, cudaMemsetAsync(Linv, 0, (size_t)np * np * sizeof(double), st));
+  FIT_CUDA(cudaMemsetAsync(Linv, 0, (size_t)np * np * sizeof(double), st));
   for (int ib = 0; ib < nblk; ++ib) {
     const int ncols = (ib + 1) * NB;   // inv(L) is lower triangular: block row ib has ib+1 nonzero block columns
     double* Ti = T;                    // 64 x ncols scratch (ld = NB) -- reuse T as 64-row matrix
@@ -547,7 +557,7 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
     if (ib > 0) {
       FIT_TRY(gemm(ctx, false, NB, ncols, ib * NB, 1.0, C + (size_t)ib * NB, np, Linv, np, 0.0, Ti, NB, 0));
     } else {
-      GSM_CUDA(ctx, cudaMemsetAsync(Ti, 0, (size_t)NB * ncols * sizeof(double), st));
+      FIT_CUDA(cudaMemsetAsync(Ti, 0, (size_t)NB * ncols * sizeof(double), st));
     }
     eye_minus_kernel<<<dim3((ncols + 127) / 128, NB), 128, 0, st>>>(Ti, NB, ib * NB, ncols);
     ctx->tim.launches++;
@@ -560,6 +570,7 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
   FIT_TRY(gemm(ctx, false, np, NB, np, 1.0, Linv, np, D, np, 0.0, T, np, 0));     // T = Linv R
   // D = Linv' T: transpose Linv into C (free after the factorisation) and reuse the NN GEMM
 #undef FIT_TRY
+#undef FIT_CUDA
   transpose_launch(Linv, C, np, st);
   ctx->tim.launches++;
   rc = gemm(ctx, false, np, NB, np, 1.0, C, np, T, np, 0.0, D, np, 0);
