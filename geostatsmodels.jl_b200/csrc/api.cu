@@ -334,6 +334,10 @@ int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value) {
     ctx->opt_shr_smax = std::max(0, std::min(3, atoi(value)));
     return GSM_OK;
   }
+  if (k == "knn_pad_smem") {
+    ctx->opt_knn_pad_smem = std::max(0, atoi(value));
+    return GSM_OK;
+  }
   if (k == "patch_nbmax") {
     ctx->opt_patch_nbmax = atoi(value);
     return GSM_OK;

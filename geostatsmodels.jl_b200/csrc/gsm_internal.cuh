@@ -144,6 +144,7 @@ struct gsm_ctx {
   int opt_shr_smax = 3;            // cap on the shared block columns of the shared-factor kernel
   double opt_bin_occupancy = 0.0;  // samples per bin cell of the neighbour search (0: default)
   int opt_patch_nbmax = 0;         // block rows of the patch kernel's block store (0: default)
+  int opt_knn_pad_smem = 0;        // extra dynamic shared memory per k-NN CTA (occupancy experiments)
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // D2H overlap
   std::string err;

@@ -22,37 +22,56 @@ namespace {
 constexpr int KNN_THREADS = 128;
 constexpr int KNN_RUN = 1;   // consecutive targets per thread (warm start only pays when lanes stay spatially coherent)
 
+// Max-heap of the best k candidates, [slot][thread] in shared memory.  Keys are the squared distances ROUNDED TO
+// FLOAT (8 bytes per slot instead of 12: six CTAs per SM instead of four, and this kernel's speed is proportional to
+// its occupancy).  Rounding is monotone, so different float keys order like the exact distances; equal float keys
+// fall back to the exact double distances recomputed from the records, then to the sample rows -- the comparison is
+// the exact total order (d2, row) in every case, and the selected set stays bit-identical to the oracle's.
 struct Heap {
-  double* d;  // [k][KNN_THREADS]
+  float* d;   // [k][KNN_THREADS] squared distance, rounded to nearest float
   int* p;     // [k][KNN_THREADS] positions into rec
   int k;
-  __device__ __forceinline__ double& D(int i) { return d[i * KNN_THREADS]; }
+  __device__ __forceinline__ float& D(int i) { return d[i * KNN_THREADS]; }
   __device__ __forceinline__ int& P(int i) { return p[i * KNN_THREADS]; }
 };
-
-// (d2a, rowa) < (d2b, rowb)?  Rows are only fetched on exact distance ties.
-__device__ __forceinline__ bool key_less(double da, int pa, double db, int pb, const int* __restrict__ sidx) {
-  if (da != db) return da < db;     // (exact distance ties are rare: lattice samples)
+struct TieCtx {   // what the exact comparison needs
+  const double4* __restrict__ rec;
+  const int* __restrict__ sidx;
+  double tx, ty, tz;
+};
+// (out of line and with by-value arguments: the rare path must not pin the context into local memory)
+__device__ __noinline__ bool key_less_exact(int pa, int pb, const double4* __restrict__ rec, const int* __restrict__ sidx,
+                                            double tx, double ty, double tz) {
+  const double4 ra = rec[pa], rb = rec[pb];
+  const double da = gsm_d2_key(ra.x, ra.y, ra.z, tx, ty, tz), db = gsm_d2_key(rb.x, rb.y, rb.z, tx, ty, tz);
+  if (da != db) return da < db;
   return sidx[pa] < sidx[pb];
 }
+// (d2a, rowa) < (d2b, rowb)?
+__device__ __forceinline__ bool key_less(float fa, int pa, float fb, int pb, const TieCtx& c) {
+  if (fa != fb) return fa < fb;
+  return key_less_exact(pa, pb, c.rec, c.sidx, c.tx, c.ty, c.tz);
+}
+// upper bound of the exact squared distance behind a float key (round-to-nearest: d2 <= next float above)
+__device__ __forceinline__ double key_upper(float f) { return (double)__uint_as_float(__float_as_uint(f) + 1u); }
 
-__device__ __forceinline__ void sift_down(Heap& hp, int i, int n, double d, int p, const int* __restrict__ sidx) {
+__device__ __forceinline__ void sift_down(Heap& hp, int i, int n, float d, int p, const TieCtx& tc) {
   // place (d,p) at the hole i of a max-heap of size n
   for (;;) {
     int c = 2 * i + 1;
     if (c >= n) break;
-    double dc = hp.D(c);
+    float dc = hp.D(c);
     int pc = hp.P(c);
     if (c + 1 < n) {
-      double dr = hp.D(c + 1);
+      float dr = hp.D(c + 1);
       int pr = hp.P(c + 1);
-      if (key_less(dc, pc, dr, pr, sidx)) {
+      if (key_less(dc, pc, dr, pr, tc)) {
         dc = dr;
         pc = pr;
         c = c + 1;
       }
     }
-    if (!key_less(d, p, dc, pc, sidx)) break;
+    if (!key_less(d, p, dc, pc, tc)) break;
     hp.D(i) = dc;
     hp.P(i) = pc;
     i = c;
@@ -61,12 +80,12 @@ __device__ __forceinline__ void sift_down(Heap& hp, int i, int n, double d, int 
   hp.P(i) = p;
 }
 
-__device__ __forceinline__ void sift_up(Heap& hp, int i, double d, int p, const int* __restrict__ sidx) {
+__device__ __forceinline__ void sift_up(Heap& hp, int i, float d, int p, const TieCtx& tc) {
   while (i > 0) {
     int par = (i - 1) >> 1;
-    double dp = hp.D(par);
+    float dp = hp.D(par);
     int pp = hp.P(par);
-    if (!key_less(dp, pp, d, p, sidx)) break;
+    if (!key_less(dp, pp, d, p, tc)) break;
     hp.D(i) = dp;
     hp.P(i) = pp;
     i = par;
@@ -85,13 +104,13 @@ struct KnnIdw {
   unsigned char* status;
 };
 
-__global__ void __launch_bounds__(KNN_THREADS)
+__global__ void __launch_bounds__(KNN_THREADS, 6)
 knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long row0, int ntx, int nty, KnnIdw idw,
            int* __restrict__ out_pos, int* __restrict__ out_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Heap hp;
-  hp.d = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
-  hp.p = reinterpret_cast<int*>(smem_raw + (size_t)k * KNN_THREADS * sizeof(double)) + threadIdx.x;
+  hp.d = reinterpret_cast<float*>(smem_raw) + threadIdx.x;
+  hp.p = reinterpret_cast<int*>(smem_raw + (size_t)k * KNN_THREADS * sizeof(float)) + threadIdx.x;
   hp.k = k;
 
   const int* __restrict__ cs = b.cell_start;
@@ -123,16 +142,20 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
   } else {
     t0 = (blockIdx.x * (long long)KNN_THREADS + threadIdx.x) * KNN_RUN;
   }
-  int cnt = 0;              // heap fill of the previous target (k when complete)
-  double prev_worst = inf;  // its k-th squared distance
+  int cnt = 0;              // heap fill (k when complete)
 
   // ---- per-target epilogue: NN value, fused local IDW, or the neighbour list (heap order) -------------------
-  auto emit = [&](const long long t, const int cnt) {
+  auto emit = [&](const long long t, const int cnt, const TieCtx& tie) {
+    // the heap keeps float keys: whatever needs a distance recomputes the exact one from the record
+    auto exact_d2 = [&](int q) -> double {
+      const double4 r = rec[q];
+      return gsm_d2_key(r.x, r.y, r.z, tie.tx, tie.ty, tie.tz);
+    };
     if (idw.on && idw.mode < 0) {
       // ---- NN model (nn.jl:47-54): the nearest sample's value; among equidistant samples the lowest row ----
       int best = -1;
       for (int i = 0; i < cnt; ++i)
-        if (best < 0 || key_less(hp.D(i), hp.P(i), hp.D(best), hp.P(best), sidx)) best = i;
+        if (best < 0 || key_less(hp.D(i), hp.P(i), hp.D(best), hp.P(best), tie)) best = i;
       idw.mean[t] = best >= 0 ? rec[hp.P(best)].w : __longlong_as_double(0x7ff8000000000000LL);
       if (idw.status) idw.status[t] = best >= 0 ? GSM_ST_OK : GSM_ST_MISSING;
       out_cnt[t] = cnt;
@@ -143,10 +166,10 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
       double sw = 0.0, swz = 0.0, hitv = 0.0;
       int nkeep = 0, hitrow = 0x7fffffff;
       for (int i = 0; i < cnt; ++i) {
-        const double d2 = hp.D(i);
+        const int q = hp.P(i);
+        const double d2 = exact_d2(q);
         if (radius > 0.0 && !(__dsqrt_rn(d2) <= radius)) continue;
         nkeep++;
-        const int q = hp.P(i);
         const double val = rec[q].w;
         if (d2 > 0.0) {
           const double w = gsm_idww::idw_weight_rt(idw.mode, d2, idw.e, idw.ei);
@@ -175,7 +198,7 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
     int nkeep = 0;
     if (radius > 0.0) {
       for (int i = 0; i < cnt; ++i)
-        if (__dsqrt_rn(hp.D(i)) <= radius) o[nkeep++] = hp.P(i);
+        if (__dsqrt_rn(exact_d2(hp.P(i))) <= radius) o[nkeep++] = hp.P(i);
     } else {
       for (int i = 0; i < cnt; ++i) o[i] = hp.P(i);
       nkeep = cnt;
@@ -227,17 +250,20 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
     double worst = inf;
     // candidate records are staged through shared memory 32 at a time: one coalesced load per chunk instead of a
     // dependent global load per candidate
-    double4* stage = reinterpret_cast<double4*>(smem_raw + (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int))) +
+    double4* stage = reinterpret_cast<double4*>(smem_raw + (size_t)k * KNN_THREADS * (sizeof(float) + sizeof(int))) +
                      (threadIdx.x >> 5) * 32;
+    const TieCtx tie{rec, sidx, tx, ty, tz};
+    // `worst`: an upper bound of the exact k-th squared distance (next float above the root's key)
     auto consider = [&](int q, const double d2) {
       if (cnt < k) {
-        sift_up(hp, cnt, d2, q, sidx);
+        sift_up(hp, cnt, __double2float_rn(d2), q, tie);
         cnt++;
-        if (cnt == k) worst = hp.D(0);
+        if (cnt == k) worst = key_upper(hp.D(0));
       } else if (d2 <= worst) {
-        if (key_less(d2, q, hp.D(0), hp.P(0), sidx)) {
-          sift_down(hp, 0, k, d2, q, sidx);
-          worst = hp.D(0);
+        const float f = __double2float_rn(d2);
+        if (key_less(f, q, hp.D(0), hp.P(0), tie)) {
+          sift_down(hp, 0, k, f, q, tie);
+          worst = key_upper(hp.D(0));
         }
       }
     };
@@ -325,7 +351,7 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
       }
       if (__all_sync(FULL, done)) break;
     }
-    if (active) emit(t0, cnt);
+    if (active) emit(t0, cnt, tie);
     return;
   }
 
@@ -336,54 +362,28 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
     gsm_target_coords(tg, tg.first + t, tx, ty, tz);
     const double tc[3] = {tx, ty, tz};
 
-    // ---- warm-start bound from the previous target's neighbours ---------------------------------
-    double bound2 = inf;
-    if (cnt == k && run > 0) {
-      double mx = 0.0;
-      for (int i = 0; i < k; ++i) {
-        const double4 r = rec[hp.P(i)];
-        mx = fmax(mx, gsm_d2_key(r.x, r.y, r.z, tx, ty, tz));
-      }
-      if (mx <= 4.0 * prev_worst) bound2 = mx;   // far jump (row wrap, scattered points): search cold
-    }
+    // (a warm start from the previous target's neighbour set was tried in round 1 and dropped: DESIGN.md section 9)
     cnt = 0;
-    double worst = inf;
+    double worst = inf;   // an upper bound of the exact k-th squared distance (next float above the root's key)
+    const TieCtx tie{rec, sidx, tx, ty, tz};
 
     auto consider = [&](int q) {
       const double4 r = rec[q];
       const double d2 = gsm_d2_key(r.x, r.y, r.z, tx, ty, tz);
-      if (d2 > bound2) return;
       if (cnt < k) {
-        sift_up(hp, cnt, d2, q, sidx);
+        sift_up(hp, cnt, __double2float_rn(d2), q, tie);
         cnt++;
-        if (cnt == k) worst = hp.D(0);
+        if (cnt == k) worst = key_upper(hp.D(0));
       } else if (d2 <= worst) {
-        if (key_less(d2, q, hp.D(0), hp.P(0), sidx)) {
-          sift_down(hp, 0, k, d2, q, sidx);
-          worst = hp.D(0);
+        const float f = __double2float_rn(d2);
+        if (key_less(f, q, hp.D(0), hp.P(0), tie)) {
+          sift_down(hp, 0, k, f, q, tie);
+          worst = key_upper(hp.D(0));
         }
       }
     };
 
-    if (bound2 < inf) {
-      // ---- warm: scan the cells overlapping the ball of radius R around the target ----------------
-      const double R = __dsqrt_ru(bound2) * (1.0 + 1e-15);
-      int lo[3], hi[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int a = (int)fmax(-1.0, fmin(floor((tc[d] - R - b.bbmin[d]) * b.inv_h), (double)b.nc[d]));
-        const int e = (int)fmax(-1.0, fmin(floor((tc[d] + R - b.bbmin[d]) * b.inv_h), (double)b.nc[d]));
-        lo[d] = min(max(a, 0), b.nc[d] - 1);
-        hi[d] = min(max(e, 0), b.nc[d] - 1);
-      }
-      for (int cz = lo[2]; cz <= hi[2]; ++cz)
-        for (int cy = lo[1]; cy <= hi[1]; ++cy) {
-          const int rowbase = b.nc[0] * (cy + b.nc[1] * cz);
-          const int beg = cs[rowbase + lo[0]];
-          const int end = cs[rowbase + hi[0] + 1];
-          for (int q = beg; q < end; ++q) consider(q);
-        }
-    } else {
+    {
       // ---- cold: Chebyshev rings around the target's cell ----------------------------------------
       int c0[3];
 #pragma unroll
@@ -462,9 +462,8 @@ knn_kernel(BinsDev b, TargetsDev tg, int k, double radius, int tiled, long long 
         }
       }
     }
-    prev_worst = (cnt == k) ? worst : inf;
 
-    emit(t, cnt);
+    emit(t, cnt, tie);
   }
 }
 
@@ -510,7 +509,8 @@ __global__ void pos_to_rows_kernel(const int* __restrict__ pos, long long total,
 static int launch_knn_impl(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, const KnnIdw& idw, int* d_pos,
                            int* d_cnt) {
   if (tg.count <= 0) return GSM_OK;
-  size_t smem = (size_t)k * KNN_THREADS * (sizeof(double) + sizeof(int)) + (KNN_THREADS / 32) * 32 * sizeof(double4);
+  size_t smem = (size_t)k * KNN_THREADS * (sizeof(float) + sizeof(int)) + (KNN_THREADS / 32) * 32 * sizeof(double4) +
+                (size_t)ctx->opt_knn_pad_smem;   // (developer option: occupancy experiments)
   GSM_CUDA(ctx, cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long blocks = (tg.count + (long long)KNN_THREADS * KNN_RUN - 1) / ((long long)KNN_THREADS * KNN_RUN);
   int tiled = 0, ntx = 1;

@@ -4,7 +4,7 @@ import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["GSM_LOCAL_IMPL"] = "shr"
+
 import __graft_entry__ as entry
 gsm = entry.load_package()
 L = gsm._lib
