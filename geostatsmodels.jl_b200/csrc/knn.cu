@@ -40,7 +40,7 @@ struct TieCtx {   // what the exact comparison needs
   double tx, ty, tz;
 };
 // (out of line and with by-value arguments: the rare path must not pin the context into local memory)
-__device__ __noinline__ bool key_less_exact(int pa, int pb, const double4* __restrict__ rec, const int* __restrict__ sidx,
+__device__ __forceinline__ bool key_less_exact(int pa, int pb, const double4* __restrict__ rec, const int* __restrict__ sidx,
                                             double tx, double ty, double tz) {
   const double4 ra = rec[pa], rb = rec[pb];
   const double da = gsm_d2_key(ra.x, ra.y, ra.z, tx, ty, tz), db = gsm_d2_key(rb.x, rb.y, rb.z, tx, ty, tz);
