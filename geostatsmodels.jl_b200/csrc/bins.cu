@@ -123,7 +123,7 @@ __global__ void sort_cells_kernel(int ncells, const int* __restrict__ cell_start
 // Average samples per cell the bins aim for.  Tuned on B200 (kNN kernel).
 static double target_occupancy(const gsm_ctx* ctx, int dim) {
   if (ctx->opt_bin_occupancy > 0.0) return ctx->opt_bin_occupancy;   // developer option "bin_occupancy" (tuning)
-  return dim >= 3 ? 2.2 : 2.0;
+  return dim >= 3 ? 2.0 : 3.0;   // (round-2 sweep with the warp-uniform search: flat optima, tools/sweep_bins.py)
 }
 
 int gsm_build_bins(gsm_ctx* ctx) {
