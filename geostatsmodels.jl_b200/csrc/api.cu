@@ -451,11 +451,16 @@ static int set_samples_impl(gsm_ctx* ctx, const double* coords, int32_t dim, int
                             bool scaled, double scale_floor, double* out_alpha, int64_t* out_nan) {
   if (!ctx) return GSM_ERR_INVALID;
   DeviceGuard g(ctx->device);
+  GsmRange nv("gsm_set_samples");
   ctx->tim = gsm_timings{};
   EventTimer et;
   cudaEvent_t e0 = et.mark(ctx->stream);
-  GSM_CHECK(gsm_upload_samples(ctx, coords, dim, n, values, scaled, scale_floor, out_alpha, out_nan));
+  {
+    GsmRange nv1("upload + _scale");
+    GSM_CHECK(gsm_upload_samples(ctx, coords, dim, n, values, scaled, scale_floor, out_alpha, out_nan));
+  }
   cudaEvent_t e1 = et.mark(ctx->stream);
+  GsmRange nv2("bins");
   GSM_CHECK(gsm_finish_samples(ctx, dim, n));
   cudaEvent_t e2 = et.mark(ctx->stream);
   GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -511,6 +516,7 @@ static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, co
     return GSM_ERR_INVALID;
   }
   DeviceGuard g(ctx->device);
+  GsmRange nv(mode == 0 ? "gsm_knn" : (mode == 1 ? "gsm_local_krige" : "gsm_idw (local)"));
   ctx->tim = gsm_timings{};
   VarioDev vd{};
   ModelDev md{};
@@ -601,6 +607,7 @@ static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, co
     }
     int* d_pos = (int*)ctx->nbr_pos.p;
     int* d_cnt = d_cnt_all + off;
+    GsmRange nvw("wave: knn + solve + download");
     cudaEvent_t a = et.mark(st);
     const bool fused_idw = mode == 2 && !onbr.dev;   // local IDW without neighbour lists: predict inside the search
     if (fused_idw)

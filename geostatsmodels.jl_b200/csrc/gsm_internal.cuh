@@ -30,6 +30,16 @@
 
 void gsm_set_error(gsm_ctx* ctx, const std::string& msg);
 
+// NVTX ranges around the phases of a call (SURVEY section 5 "tracing"): header-only NVTX3, a no-op unless a profiler
+// (nsys / ncu --nvtx) has injected itself into the process.
+#include <nvtx3/nvToolsExt.h>
+struct GsmRange {
+  explicit GsmRange(const char* name) { nvtxRangePushA(name); }
+  ~GsmRange() { nvtxRangePop(); }
+  GsmRange(const GsmRange&) = delete;
+  GsmRange& operator=(const GsmRange&) = delete;
+};
+
 // A pivot of the covariance block at or below GSM_PIVOT_RTOL * sill, or a pivot of the drift Schur complement at
 // or below GSM_SCHUR_RTOL times its own diagonal entry, marks the system singular (coincident samples, fewer points
 // than drift terms).  The reference's status(fit) = issuccess(bunchkaufman!(...)) (krig.jl:152) catches these

@@ -432,6 +432,7 @@ int gsm_global_krige_fit(gsm_ctx* ctx, const gsm_variogram* vario, const gsm_mod
     return GSM_ERR_NO_SAMPLES;
   }
   GSM_CHECK(gsm_check_vario(ctx, vario));
+  GsmRange nv("gsm_global_krige_fit");
   if (!model || model->kind < 0 || model->kind > 2 ||
       (model->kind == GSM_KRIG_UNIVERSAL && (model->ndrift < 1 || model->ndrift > GSM_MAX_DRIFT))) {
     gsm_set_error(ctx, "invalid Kriging model descriptor");

@@ -165,6 +165,7 @@ void merge_summaries(gsm_multi* mg) {
 int set_samples_multi(gsm_multi* mg, const double* coords, int32_t dim, int64_t n, const double* values, bool scaled,
                       double scale_floor, double* out_alpha, int64_t* out_nan) {
   if (!mg) return GSM_ERR_INVALID;
+  GsmRange nv("gsm_multi_set_samples (upload + ncclBroadcast + bins)");
   const int nd = (int)mg->ctx.size();
   mg->tim = gsm_multi_timings{};
   const double t0 = now_ms();
@@ -335,6 +336,7 @@ int gsm_multi_slab(const gsm_multi* mg, const gsm_targets* targets, int32_t i, i
 static int multi_predict(gsm_multi* mg, const gsm_targets* targets, bool outputs_ok,
                          const std::function<int(int, gsm_ctx*, const gsm_targets*, long long)>& call) {
   if (!mg || !targets) return GSM_ERR_INVALID;
+  GsmRange nv("gsm_multi predict (slab per device)");
   if (mg->n <= 0) return fail(mg, GSM_ERR_NO_SAMPLES, "no samples: call gsm_multi_set_samples first");
   if (!outputs_ok) return fail(mg, GSM_ERR_INVALID, "multi-GPU outputs must be HOST buffers (pinned for direct DMA)");
   const int nd = (int)mg->ctx.size();
