@@ -127,7 +127,7 @@ class CoregionalizedVariogram:
     every sample the cokriging system (C0 (x) B) decouples: the weights of every variable are the scalar Kriging
     weights of gamma0 and the covariance of the prediction is B times the scalar variance ("autokrigeability" of the
     proportional model; tests/test_cokriging.py checks it against the reference's full (nobs nvar + ncon nvar) system
-    restated in oracle/).  The GPU path therefore serves this form with one univariate solve per variable."""
+    restated by the CPU test oracle).  The GPU path therefore serves this form with one univariate solve per variable."""
 
     def __init__(self, B, base):
         self.B = np.asarray(B, dtype=np.float64)
