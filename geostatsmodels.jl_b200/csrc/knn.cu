@@ -56,21 +56,21 @@ __device__ __forceinline__ bool key_less(float fa, int pa, float fb, int pb, con
 __device__ __forceinline__ double key_upper(float f) { return (double)__uint_as_float(__float_as_uint(f) + 1u); }
 
 __device__ __forceinline__ void sift_down(Heap& hp, int i, int n, float d, int p, const TieCtx& tc) {
-  // place (d,p) at the hole i of a max-heap of size n
+  // place (d,p) at the hole i of a max-heap of size n.  Positions are only loaded when an entry moves (or on a float
+  // tie): two key loads and one position load per level.
   for (;;) {
     int c = 2 * i + 1;
     if (c >= n) break;
     float dc = hp.D(c);
-    int pc = hp.P(c);
     if (c + 1 < n) {
-      float dr = hp.D(c + 1);
-      int pr = hp.P(c + 1);
-      if (key_less(dc, pc, dr, pr, tc)) {
+      const float dr = hp.D(c + 1);
+      const bool right = (dc != dr) ? dc < dr : key_less_exact(hp.P(c), hp.P(c + 1), tc.rec, tc.sidx, tc.tx, tc.ty, tc.tz);
+      if (right) {
         dc = dr;
-        pc = pr;
         c = c + 1;
       }
     }
+    const int pc = hp.P(c);
     if (!key_less(d, p, dc, pc, tc)) break;
     hp.D(i) = dc;
     hp.P(i) = pc;
