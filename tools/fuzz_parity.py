@@ -77,8 +77,11 @@ def one(seed):
         mu_q, var_q, ok_q = mu, var, st == 0
     try:
         got = gsm.fitpredict(gm, tab, grid, prob=True, neighborhood=nbh, count=-1 if count is None else count, **kw).z
-    except ValueError as ex:   # non-positive variance: the oracle must see one too
-        return bool(np.any((var <= 0) & (st == 0))), desc + f" sill={sill} [{ex}]"
+    except ValueError as ex:
+        # non-positive variance (the reference throws where Normal(mean, var) sees one).  At an exact hit the true
+        # variance is 1e-10 while both solvers carry rounding noise of ~1e-15 * sill * condition: with sill = 1e13 the
+        # sign of the computed value is luck on either side, so the oracle only has to be AT rounding level somewhere
+        return bool(np.any((var <= 1e-9 * max(sill, 1.0)) & (st == 0))), desc + f" sill={sill} [{ex}]"
     desc += f" sill={sill:g}"
     gmu, gvar = np.ma.filled(got.mu, np.nan), np.ma.filled(got.sigma, np.nan)
     bad_o = st != 0
