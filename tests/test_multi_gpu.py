@@ -73,3 +73,42 @@ def test_multi_slabs_partition_idw_global_and_shards(gsm, oracle, ndev):
     if ndev > 1:     # (a one-device list goes through the plain context)
         t = mc.timings()
         assert t["wall_ms"] > 0 and t["predict_ms"] > 0
+
+
+def test_multi_and_option_error_paths(gsm):
+    """Error behaviour of the round-2 entry points: codes, messages, no exceptions across the C ABI."""
+    import ctypes as C
+    L = gsm._lib
+    lib = L.load()
+    h = C.c_void_p()
+    # duplicate / out-of-range device ordinals
+    devs = (C.c_int32 * 2)(0, 0)
+    assert lib.gsm_multi_create(devs, 2, C.byref(h)) == L.GSM_ERR_INVALID and b"duplicate" in lib.gsm_multi_last_error(None)
+    devs = (C.c_int32 * 1)(99)
+    assert lib.gsm_multi_create(devs, 1, C.byref(h)) == L.GSM_ERR_INVALID
+    assert lib.gsm_multi_create(devs, 0, C.byref(h)) == L.GSM_ERR_INVALID
+    # predict before set_samples
+    mc = L.MultiContext([0])
+    t = L.Context.grid_targets((0.0, 0.0), (1.0, 1.0), (8, 8))
+    with pytest.raises(gsm.GsmError) as e:
+        mc.local_krige(L.make_variogram(1, 1, 0, 1), L.make_model(L.GSM_KRIG_ORDINARY), t, 8)
+    assert e.value.code == L.GSM_ERR_NO_SAMPLES
+    mc.close()
+    # options: unknown key / value rejected, known ones accepted and effective
+    c = gsm.Context(0)
+    with pytest.raises(gsm.GsmError):
+        c.set_option("no_such_option", 1)
+    with pytest.raises(gsm.GsmError):
+        c.set_option("local_impl", "fastest")
+    rng = np.random.default_rng(1)
+    X = rng.uniform(0, 40, size=(3000, 2))
+    z = rng.standard_normal(3000)
+    model = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=8.0, nugget=0.1))
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    grid = gsm.CartesianGrid((0.0, 0.0), (40.0, 40.0), dims=(96, 80))
+    ref = gsm.fitpredict(model, tab, grid, maxneighbors=32, prob=True, ctx=c).z
+    for impl in ("patch", "patch2", "pipe", "simt", "shr", "auto"):
+        c.set_option("local_impl", impl)
+        got = gsm.fitpredict(model, tab, grid, maxneighbors=32, prob=True, ctx=c).z
+        assert np.allclose(got.mu, ref.mu, rtol=1e-11, atol=1e-12) and np.allclose(got.sigma, ref.sigma, rtol=1e-11, atol=1e-12), impl
+    c.close()
