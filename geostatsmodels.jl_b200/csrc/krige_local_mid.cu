@@ -16,6 +16,8 @@
 // It replaces the CTA-per-system SIMT kernel (krige_local_big.cu, kept as GSM_LOCAL_IMPL=big) as the k > 32 path.
 #include <algorithm>
 
+#include <type_traits>
+
 #include "gsm_internal.cuh"
 #include "krige_cov_fast.cuh"
 
@@ -36,6 +38,29 @@ __device__ __forceinline__ double rsqrt_m(double d) {
   const double e = fma(-(d * y), y, 1.0);
   const double p = e * fma(e, 0.375, 0.5);
   return fma(y, p, y);
+}
+
+// sill - gamma(h) from a squared distance with the variogram kind as a compile-time constant (krige_cov_fast.cuh holds
+// the run-time form; same arithmetic)
+template <int KIND>
+__device__ __forceinline__ double cov_kind_mid(const gsm_cov::CovFast& c, double d2) {
+  const double d2c = __hiloint2double(max(__double2hiint(d2), 0x03e00000), __double2loint(d2));
+  double v;
+  if (KIND == GSM_VARIO_SPHERICAL) {
+    const double t2 = d2 * c.inv_r2;
+    const double y = gsm_cov::fast_rsqrt(d2c);
+    const double t = (d2 * c.inv_r) * y;
+    v = fma(t, fma(c.k2, t2, c.k1), c.c1);
+    v = (d2 < c.range2) ? v : c.cfar;
+  } else if (KIND == GSM_VARIO_GAUSSIAN) {
+    const double t2 = d2 * c.inv_r2;
+    v = c.sill - (c.cs * (1.0 - exp(-3.0 * t2)) + (c.sill - c.c1));
+  } else {
+    const double y = gsm_cov::fast_rsqrt(d2c);
+    const double t = (d2 * c.inv_r) * y;
+    v = c.sill - (c.cs * (1.0 - exp(-3.0 * t)) + (c.sill - c.c1));
+  }
+  return (d2 > 0.0) ? v : c.sill;
 }
 
 // Warp-cooperative inverse Cholesky factor of an 8x8 SPD block in fragment layout (lane (g,t) owns A[g][2t],
@@ -156,7 +181,35 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
 
     // ---- assemble the blocks (fragment layout); empty slots are identity rows / columns ----
     int bcount = 0;
-    for (int I = 0; I < nbc; ++I)
+    const bool fullsys = n == 8 * nbc && !v.general;
+    if (fullsys) {
+      // every slot live, one of the three isotropic families (the common case): row coordinates hoisted per block row,
+      // the two columns of a lane loaded as pairs, no padding tests, the variogram kind compiled in
+      auto fast = [&](auto kind_tag) __attribute__((always_inline)) {
+        constexpr int KIND = decltype(kind_tag)::value;
+        for (int I = 0; I < nbc; ++I) {
+          const double rx = S.px[8 * I + g], ry = S.py[8 * I + g], rz = S.pz[8 * I + g];
+          for (int J = 0; J <= I; ++J) {
+            if (((bcount++) & 1) != h) continue;
+            const double2 cx = *reinterpret_cast<const double2*>(&S.px[8 * J + 2 * t]);
+            const double2 cy = *reinterpret_cast<const double2*>(&S.py[8 * J + 2 * t]);
+            const double2 cz = *reinterpret_cast<const double2*>(&S.pz[8 * J + 2 * t]);
+            const double dx0 = rx - cx.x, dy0 = ry - cy.x, dz0 = rz - cz.x, dx1 = rx - cx.y, dy1 = ry - cy.y, dz1 = rz - cz.y;
+            double e0 = cov_kind_mid<KIND>(cf, fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0)));
+            double e1 = cov_kind_mid<KIND>(cf, fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1)));
+            if (I == J) {
+              e0 = g == 2 * t ? v.sill : e0;
+              e1 = g == 2 * t + 1 ? v.sill : e1;
+            }
+            put(S.blk[lowidx(I, J)], make_double2(e0, e1));
+          }
+        }
+      };
+      if (cf.kind == GSM_VARIO_SPHERICAL) fast(std::integral_constant<int, GSM_VARIO_SPHERICAL>{});
+      else if (cf.kind == GSM_VARIO_GAUSSIAN) fast(std::integral_constant<int, GSM_VARIO_GAUSSIAN>{});
+      else fast(std::integral_constant<int, GSM_VARIO_EXPONENTIAL>{});
+    }
+    for (int I = 0; I < (fullsys ? 0 : nbc); ++I)
       for (int J = 0; J <= I; ++J) {
         if (((bcount++) & 1) != h) continue;
         const int row = 8 * I + g, c0 = 8 * J + 2 * t;
