@@ -19,9 +19,8 @@ for s in ([0.03, 0.1, 0.2, 0.35, 0.5, 1.0] if dim == 2 else [0.02, 0.06, 0.15, 0
     t = gsm.Context.grid_targets((0,) * dim, (a,) * dim, (g,) * dim)
     om = torch.empty(M, dtype=torch.float64, device="cuda"); ov = torch.empty_like(om); ost = torch.empty(M, dtype=torch.uint8, device="cuda")
     out = []
-    for impl in ("pipe", "shr", None):
-        if impl is None: os.environ.pop("GSM_LOCAL_IMPL", None)
-        else: os.environ["GSM_LOCAL_IMPL"] = impl
+    for impl in ("pipe", "shr", "auto"):
+        ctx.set_option("local_impl", impl)
         for _ in range(3):
             ctx.local_krige(v, m, t, 32, out_mean=om, out_var=ov, out_status=ost)
         out.append(round(ctx.timings()["solve_ms"], 2))
