@@ -19,6 +19,7 @@ GSM_ST_OK, GSM_ST_MISSING, GSM_ST_SINGULAR = 0, 1, 2
 GSM_VARIO_GAUSSIAN, GSM_VARIO_SPHERICAL, GSM_VARIO_EXPONENTIAL = 0, 1, 2
 GSM_VARIO_CUBIC, GSM_VARIO_PENTASPHERICAL, GSM_VARIO_SINEHOLE, GSM_VARIO_CIRCULAR, GSM_VARIO_NUGGET = 3, 4, 5, 6, 7
 GSM_MAX_STRUCTURES = 4
+GSM_MAX_BLOCK_POINTS = 512
 GSM_KRIG_SIMPLE, GSM_KRIG_ORDINARY, GSM_KRIG_UNIVERSAL = 0, 1, 2
 GSM_TARGETS_GRID, GSM_TARGETS_POINTS = 0, 1
 
@@ -26,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "gsm_abi_version", "gsm_create", "gsm_destroy", "gsm_last_error", "gsm_get_timings", "gsm_get_summary", "gsm_synchronize",
     "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_set_samples_scaled", "gsm_knn", "gsm_local_krige",
     "gsm_global_krige_fit", "gsm_global_krige_status", "gsm_global_krige_predict", "gsm_global_krige_free",
-    "gsm_idw", "gsm_nn", "gsm_measure_fp64_peak", "gsm_set_option",
+    "gsm_idw", "gsm_nn", "gsm_measure_fp64_peak", "gsm_set_option", "gsm_set_block_support",
     "gsm_multi_create", "gsm_multi_destroy", "gsm_multi_last_error", "gsm_multi_device_count", "gsm_multi_context",
     "gsm_multi_get_timings", "gsm_multi_get_summary", "gsm_multi_set_samples", "gsm_multi_set_samples_scaled",
     "gsm_multi_slab", "gsm_multi_local_krige", "gsm_multi_idw", "gsm_multi_global_krige",
@@ -126,6 +127,7 @@ def load():
     lib.gsm_nn.argtypes = [vp, P(Targets), vp]
     lib.gsm_measure_fp64_peak.argtypes = [vp, P(dbl), P(dbl)]
     lib.gsm_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
+    lib.gsm_set_block_support.argtypes = [vp, C.c_void_p, C.c_int32, C.c_int32]
     lib.gsm_multi_create.argtypes = [P(i32), i32, P(vp)]
     lib.gsm_multi_destroy.argtypes = [vp]
     lib.gsm_multi_last_error.argtypes = [vp]
@@ -281,6 +283,17 @@ class Context:
     def set_option(self, key: str, value) -> None:
         """developer options (gsm_set_option): local_impl, shr_smax, bin_occupancy"""
         self._check(self._lib.gsm_set_option(self._h, str(key).encode(), str(value).encode()))
+
+    def set_block_support(self, offsets=None) -> None:
+        """gsm_set_block_support: the (nq, dim) points, relative to the centroid and in sample coordinates, that stand
+        for every target of the following Kriging calls; None or an empty table returns to point support."""
+        if offsets is None or len(offsets) == 0:
+            self._check(self._lib.gsm_set_block_support(self._h, None, 0, 0))
+            return
+        off = np.ascontiguousarray(offsets, dtype=np.float64)
+        if off.ndim == 1:
+            off = off[:, None]
+        self._check(self._lib.gsm_set_block_support(self._h, off.ctypes.data, off.shape[1], off.shape[0]))
 
     def set_samples(self, coords, values, dim=None, n=None):
         """coords: (n, dim) float64 C-order numpy array, or a device pointer / torch tensor with dim, n."""
@@ -456,6 +469,14 @@ class MultiContext:
     def set_option(self, key, value) -> None:
         for i in range(len(self.devices)):
             rc = self._lib.gsm_set_option(self._lib.gsm_multi_context(self._h, i), str(key).encode(), str(value).encode())
+            self._check(rc)
+
+    def set_block_support(self, offsets=None) -> None:
+        nq = 0 if offsets is None else len(offsets)
+        off = np.ascontiguousarray(offsets, dtype=np.float64).reshape(nq, -1) if nq else None
+        for i in range(len(self.devices)):
+            rc = self._lib.gsm_set_block_support(self._lib.gsm_multi_context(self._h, i),
+                                                 off.ctypes.data if nq else None, off.shape[1] if nq else 0, nq)
             self._check(rc)
 
     def slab(self, targets: Targets, i: int):

@@ -25,6 +25,7 @@ __all__ = [
     "SineHoleVariogram", "CircularVariogram", "NuggetEffect", "CompositeVariogram", "PointSet", "CartesianGrid", "GeoTable",
     "georef", "IDW", "NN", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
     "predict", "predictprob", "status", "fitpredict", "default_context", "multi_context", "set_default_device", "Dirac",
+    "Box", "Quadrangle", "block_points",
 ]
 
 
@@ -248,6 +249,34 @@ class CartesianGrid:
         lo = np.asarray(self.origin)
         hi = lo + np.asarray(self.dims, dtype=np.float64) * np.asarray(self.spacing)
         return float(max(np.abs(lo).max(), np.abs(hi).max()))
+
+
+class Box:
+    """Box(lower, upper): an axis-aligned segment / quadrangle / hexahedron as a prediction target with volume support
+    (the `Quadrangle((0,0),(1,0),(1,1),(0,1))` of test/krig.jl:231 is Box((0, 0), (1, 1)))."""
+
+    def __init__(self, lower, upper):
+        self.lower = tuple(float(x) for x in lower)
+        self.upper = tuple(float(x) for x in upper)
+        if len(self.lower) != len(self.upper) or not 1 <= len(self.lower) <= 3:
+            raise ValueError("Box needs two corners of the same dimension (1 to 3)")
+
+    @property
+    def sides(self):
+        return tuple(h - l for l, h in zip(self.lower, self.upper))
+
+    def centroid(self):
+        return np.array([(l + h) / 2 for l, h in zip(self.lower, self.upper)])
+
+
+def Quadrangle(a, b, c, d) -> "Box":
+    """Quadrangle(a, b, c, d) with axis-aligned sides, as a Box (other quadrangles are not claimed)."""
+    P = np.asarray([a, b, c, d], dtype=np.float64)
+    lo, hi = P.min(axis=0), P.max(axis=0)
+    corners = {(x, y) for x in (lo[0], hi[0]) for y in (lo[1], hi[1])}
+    if P.shape != (4, 2) or {tuple(p_) for p_ in P} != corners:
+        raise NotImplementedError("only axis-aligned quadrangles are claimed by the GPU path")
+    return Box(lo, hi)
 
 
 class GeoTable:
@@ -562,28 +591,46 @@ def _check_vars(fitted, var):
     return names[0], scalar
 
 
-def predict(fitted, var, g):
-    """predict(fitted, var, g) (krig.jl:215-219; idw.jl:55)."""
-    _, scalar = _check_vars(fitted, var)
+def _target_of(fitted, g):
+    """point target at the centroid of g, and the block offsets when g has a volume (krig.jl:316-361 on a geometry)"""
+    block = None
+    if isinstance(g, Box):
+        if isinstance(fitted, FittedKriging):
+            block = block_points(g, fitted.model._range()) * fitted._alpha
+        g = g.centroid()
     p = _as_point(g, fitted._ctx.dim) * fitted._alpha
-    t = _lib.Context.point_targets(p)
+    return _lib.Context.point_targets(p), block
+
+
+def _krige_at(fitted, t, block, want_var):
+    fitted._ctx.set_block_support(block)
+    try:
+        return fitted._gfit.predict(t, want_var=want_var)
+    finally:
+        if block is not None:
+            fitted._ctx.set_block_support(None)
+
+
+def predict(fitted, var, g):
+    """predict(fitted, var, g) (krig.jl:215-219; idw.jl:55); g: a point or a Box (change of support)."""
+    _, scalar = _check_vars(fitted, var)
+    t, block = _target_of(fitted, g)
     if isinstance(fitted, FittedIDW):
         mean, _ = fitted._ctx.idw(fitted.model.exponent, t)
     else:
-        mean, _ = fitted._gfit.predict(t, want_var=False)
+        mean, _ = _krige_at(fitted, t, block, False)
     return float(mean[0]) if scalar else [float(mean[0])]
 
 
 def predictprob(fitted, var, g):
     """predictprob(fitted, var, g): Normal(mu, sqrt(var)) for Kriging (krig.jl:223-229)."""
     _, scalar = _check_vars(fitted, var)
-    p = _as_point(g, fitted._ctx.dim) * fitted._alpha
-    t = _lib.Context.point_targets(p)
+    t, block = _target_of(fitted, g)
     if isinstance(fitted, FittedIDW):
         mean, _ = fitted._ctx.idw(fitted.model.exponent, t)      # predictprob = Dirac(predict) (idw.jl:57)
         d = Dirac(float(mean[0]))
         return d if scalar else [d]
-    mean, var_ = fitted._gfit.predict(t, want_var=True)
+    mean, var_ = _krige_at(fitted, t, block, True)
     if var_[0] < 0:
         raise ValueError("DomainError: sqrt of negative variance")  # krig.jl:228
     d = Normal(float(mean[0]), math.sqrt(float(var_[0])))
@@ -608,9 +655,32 @@ def _targets_for(dom, alpha, first=0, count=-1):
     return _lib.Context.point_targets(dom.coords * alpha, first=first, count=count)
 
 
+def block_points(dom, vrange: float) -> np.ndarray:
+    """Offsets (nq, dim) from the centroid of the points that stand for one cell of the grid ``dom`` (or for a ``Box``)
+    under change of support.
+
+    Which points represent a geometry is decided upstream in GeoStatsFunctions (``f(point, geometry)`` behind
+    ``pairwise!``, krig.jl:125,350), not in the reference tree.  The rule restated here is the recalled one: spacing
+    ``s = min(range, shortest side) / 3``, ``n_d = ceil(side_d / s)`` points per dimension on the regular lattice that
+    includes the cell boundary (Meshes ``RegularSampling`` on a non-periodic parametrisation).  The only thing the
+    reference's tests pin about block support is ``var >= 0`` (test/krig.jl:221-242), so parity of the rule itself is
+    unpinned; a caller who knows better passes ``block_offsets=`` to fitpredict."""
+    sides = np.abs(np.asarray(dom.sides if isinstance(dom, Box) else dom.spacing, dtype=np.float64))
+    pos = sides[sides > 0]
+    short = float(pos.min()) if len(pos) else 1.0
+    s = (min(float(vrange), short) if (vrange > 0 and math.isfinite(vrange)) else short) / 3.0
+    axes = []
+    for side in sides:
+        n = max(int(math.ceil(side / s - 1e-9)), 1) if side > 0 else 1
+        axes.append(np.linspace(-0.5 * side, 0.5 * side, n) if n > 1 else np.zeros(1))
+    mesh = np.meshgrid(*axes, indexing="ij")
+    # first coordinate fastest, like the element order of the grid itself
+    return np.stack([m_.ravel(order="F") for m_ in mesh], axis=1)
+
+
 def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=True, minneighbors=1,
                maxneighbors=10, neighborhood=None, distance="euclidean", device=None, devices=None, first=0,
-               count=-1, ctx=None, out=None, _device_samples=None):
+               count=-1, ctx=None, out=None, block_offsets=None, _device_samples=None):
     """fitpredict(model, geotable, domain; options) (models.jl:102-129).
 
     ``first``/``count`` (not in the reference) select a contiguous shard of the target index for
@@ -618,12 +688,21 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     ``out`` may hold preallocated (pinned) arrays ``mean`` / ``var`` / ``status`` the results DMA into.
     ``devices=[0, 1, ...]`` (not in the reference) runs the call on several GPUs of the box through the multi-GPU
     C ABI (gsm_multi_*): samples replicated by one NCCL broadcast, target slabs, one host thread per device."""
-    if not point:
-        raise NotImplementedError("change of support (point=false) is not claimed by the GPU path")
     if distance != "euclidean":
         raise NotImplementedError("only the Euclidean distance is claimed by the GPU path")
     if not isinstance(dom, (PointSet, CartesianGrid)):
         dom = PointSet(dom)
+    # change of support (point=false, models.jl:114-115,136): the elements of a PointSet are points anyway, and IDW / NN
+    # only look at centroids (idw.jl:82, nn.jl); a Kriging model on a grid averages the right-hand side over the cell
+    block = None
+    if not point and isinstance(dom, CartesianGrid) and isinstance(model, _KrigingModel):
+        if neighbors and _clamp_max(maxneighbors, len(_pointset_of(data.domain))) > 32:
+            raise NotImplementedError("change of support is claimed for maxneighbors <= 32")
+        block = block_points(dom, model._range()) if block_offsets is None else np.asarray(block_offsets, dtype=np.float64)
+        if block.ndim != 2 or block.shape[1] != dom.dim or len(block) < 1:
+            raise ValueError("block_offsets must be (nq, dim) with nq >= 1")
+        if len(block) > _lib.GSM_MAX_BLOCK_POINTS:
+            raise NotImplementedError("change of support with more than GSM_MAX_BLOCK_POINTS points per cell is not claimed")
     if _nvariables(model) > 1:
         # CoKriging with a proportional covariance B * gamma0 and isotopic data: one univariate solve per variable
         _checkcompat(model, data)
@@ -634,7 +713,7 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             one = fitpredict(_marginal_model(model, p_), GeoTable({name: data.table[name]}, data.domain), dom, point=point,
                              prob=prob, neighbors=neighbors, minneighbors=minneighbors, maxneighbors=maxneighbors,
                              neighborhood=neighborhood, distance=distance, device=device, devices=devices, first=first,
-                             count=count, ctx=ctx)
+                             count=count, ctx=ctx, block_offsets=block_offsets)
             cols[name] = one.table[name]
         pred = GeoTable.__new__(GeoTable)
         pred.table = cols
@@ -703,6 +782,7 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             col = Dirac(col)                               # predictprob = Dirac(predict) (idw.jl:57)
     else:
         sm = kmodel._scaled(alpha)
+        ctx.set_block_support(None if block is None else block * alpha)
         if neighbors:
             mean, var, st, _ = ctx.local_krige(sm.fun._c(), sm._c(), t, _clamp_max(maxneighbors, nobs),
                                                minneighbors, radius, want_var=prob, out_mean=out.get("mean"),
@@ -719,6 +799,8 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             if not gfit.status():
                 st[:] = _lib.GSM_ST_SINGULAR           # status(fitted) == false (krig.jl:49-52)
             gfit.close()
+        if block is not None:
+            ctx.set_block_support(None)
         # the library reduces the status / variance columns on the device (gsm_get_summary): the host only
         # scans them (tens of MB) when that is not available
         sm = ctx.summary() if neighbors else {"total": -1}

@@ -291,7 +291,7 @@ int gsm_destroy(gsm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->coords, &ctx->values, &ctx->rec, &ctx->sidx, &ctx->cell_of, &ctx->cell_start,
-                    &ctx->cell_fill, &ctx->cub_tmp, &ctx->red, &ctx->nbr_pos, &ctx->nbr_cnt, &ctx->job_idx, &ctx->summ_dev, &ctx->glob_R, &ctx->glob_acc, &ctx->out_mean,
+                    &ctx->cell_fill, &ctx->cub_tmp, &ctx->red, &ctx->block_off, &ctx->nbr_pos, &ctx->nbr_cnt, &ctx->job_idx, &ctx->summ_dev, &ctx->glob_R, &ctx->glob_acc, &ctx->out_mean,
                     &ctx->out_var, &ctx->out_status, &ctx->out_nbr, &ctx->tgt_points};
   for (DevBuf* b : bufs) free_buf(*b);
   cudaStreamDestroy(ctx->stream);
@@ -350,6 +350,36 @@ int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value) {
   return GSM_ERR_INVALID;
 }
 
+int gsm_set_block_support(gsm_ctx* ctx, const double* offsets, int dim, int nq) {
+  if (!ctx) return GSM_ERR_INVALID;
+  if (nq == 0) {
+    ctx->block_nq = 0;
+    return GSM_OK;
+  }
+  if (!offsets || dim < 1 || dim > 3 || nq < 0 || nq > GSM_MAX_BLOCK_POINTS) {
+    gsm_set_error(ctx, "gsm_set_block_support: need offsets, 1 <= dim <= 3 and 0 <= nq <= GSM_MAX_BLOCK_POINTS");
+    return GSM_ERR_INVALID;
+  }
+  std::vector<double> off((size_t)nq * 3, 0.0);
+  for (int q = 0; q < nq; ++q)
+    for (int d = 0; d < dim; ++d) {
+      const double o = offsets[(size_t)q * dim + d];
+      if (!std::isfinite(o)) {
+        gsm_set_error(ctx, "gsm_set_block_support: offsets must be finite");
+        return GSM_ERR_INVALID;
+      }
+      off[(size_t)q * 3 + d] = o;
+    }
+  DeviceGuard g(ctx->device);
+  GSM_CHECK(gsm_reserve(ctx, ctx->block_off, off.size() * sizeof(double)));
+  // (pageable source: cudaMemcpyAsync returns after staging it, so `off` may go out of scope)
+  GSM_CUDA(ctx, cudaMemcpyAsync(ctx->block_off.p, off.data(), off.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->block_nq = nq;
+  return GSM_OK;
+}
+
 int gsm_synchronize(gsm_ctx* ctx) {
   if (!ctx) return GSM_ERR_INVALID;
   DeviceGuard g(ctx->device);
@@ -392,6 +422,41 @@ int gsm_check_vario(gsm_ctx* ctx, const gsm_variogram* v) {
     gsm_set_error(ctx, "invalid variogram descriptor");
     return GSM_ERR_INVALID;
   }
+  return GSM_OK;
+}
+
+namespace {
+// covzero of a block target: mean covariance over all pairs of its points (krig.jl:295-301 with
+// GeoStatsFunctions' f(g0, g0)); one CTA, fixed summation order
+__global__ void __launch_bounds__(256) block_c0_kernel(VarioDev v, const double* __restrict__ off, int nq,
+                                                        double* __restrict__ out) {
+  __shared__ double part[256];
+  double s = 0.0;
+  for (int e = threadIdx.x; e < nq * nq; e += 256) {
+    const int p = e / nq, q = e - p * nq;
+    s += gsm_cov_vec(v, off[3 * p] - off[3 * q], off[3 * p + 1] - off[3 * q + 1], off[3 * p + 2] - off[3 * q + 2]);
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = part[0] / ((double)nq * (double)nq);
+}
+}  // namespace
+
+int gsm_block_prepare(gsm_ctx* ctx, const VarioDev& v) {
+  ctx->block_cur = BlockDev{0, nullptr, v.sill};
+  if (ctx->block_nq <= 0) return GSM_OK;
+  GSM_CHECK(gsm_reserve(ctx, ctx->red, 64 * sizeof(double)));
+  double* d_c0 = (double*)ctx->red.p;
+  block_c0_kernel<<<1, 256, 0, ctx->stream>>>(v, (const double*)ctx->block_off.p, ctx->block_nq, d_c0);
+  GSM_CUDA(ctx, cudaGetLastError());
+  double c0 = 0.0;
+  GSM_CUDA(ctx, cudaMemcpyAsync(&c0, d_c0, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GSM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->block_cur = BlockDev{ctx->block_nq, (const double*)ctx->block_off.p, c0};
   return GSM_OK;
 }
 
@@ -524,6 +589,7 @@ static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, co
     GSM_CHECK(check_vario(ctx, vario));
     vd = make_vario(*vario);
     GSM_CHECK(make_model(ctx, model, ctx->dim, md));
+    GSM_CHECK(gsm_block_prepare(ctx, vd));
     if (!out_mean) {
       gsm_set_error(ctx, "out_mean is required");
       return GSM_ERR_INVALID;

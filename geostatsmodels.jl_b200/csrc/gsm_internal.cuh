@@ -147,6 +147,13 @@ struct DevBuf {
 // gsm_set_option(ctx, "local_impl", ...): which local-Kriging kernel serves k <= 32 (default: dispatch by shape)
 enum { GSM_IMPL_AUTO = 0, GSM_IMPL_SHR = 1, GSM_IMPL_PIPE = 2, GSM_IMPL_SIMT = 3, GSM_IMPL_PATCH = 4, GSM_IMPL_PATCH2 = 5 };
 
+// Change of support (gsm_set_block_support): the points that stand for a target, relative to its centroid.
+struct BlockDev {
+  int nq;              // 0: point support
+  const double* off;   // nq x 3 (z zero-padded in 2-D), device
+  double c0;           // covzero: mean covariance over the nq^2 pairs (the total sill for a point, krig.jl:295-301)
+};
+
 struct gsm_ctx {
   int device = 0;
   // developer options (gsm_set_option; never read from the environment)
@@ -176,6 +183,11 @@ struct gsm_ctx {
   BinsDev bins{};
   double sample_mean = 0.0;
   long long n_missing = 0;   // samples whose value is NaN (`missing`)
+
+  // change of support
+  int block_nq = 0;
+  DevBuf block_off;        // block_nq x 3 doubles
+  BlockDev block_cur{};    // descriptor of the running call (gsm_block_prepare)
 
   // per-call scratch
   DevBuf nbr_pos;     // chunk x k int : positions into rec
@@ -212,6 +224,8 @@ bool gsm_is_device_ptr(const void* p);
 // ---------------------------------------------------------------------------------------------
 int gsm_build_bins(gsm_ctx* ctx);
 int gsm_check_vario(gsm_ctx* ctx, const gsm_variogram* v);
+// fills ctx->block_cur for a call with variogram v (covzero of the block evaluated on the device); point support: nq = 0
+int gsm_block_prepare(gsm_ctx* ctx, const VarioDev& v);
 int gsm_upload_samples(gsm_ctx* ctx, const double* coords, int32_t dim, int64_t n, const double* values, bool scaled,
                        double scale_floor, double* out_alpha, int64_t* out_nan);
 int gsm_finish_samples(gsm_ctx* ctx, int32_t dim, int64_t n);
@@ -340,6 +354,15 @@ static __device__ __noinline__ double gsm_cov_general(const VarioDev& v, double 
 __device__ __forceinline__ double gsm_cov_vec(const VarioDev& v, double dx, double dy, double dz) {
   if (v.general) return gsm_cov_general(v, dx, dy, dz);
   return gsm_cov_d2(v, dx * dx + dy * dy + dz * dz);
+}
+
+// Mean covariance between a sample and the points of a block target; (dx, dy, dz) = sample - centroid
+// (GeoStatsFunctions' f(point, geometry) behind pairwise!, krig.jl:350; summed in offset order).
+static __device__ __noinline__ double gsm_cov_block(const VarioDev& v, const BlockDev& bk, double dx, double dy, double dz) {
+  double s = 0.0;
+  for (int q = 0; q < bk.nq; ++q)
+    s += gsm_cov_vec(v, dx - bk.off[3 * q], dy - bk.off[3 * q + 1], dz - bk.off[3 * q + 2]);
+  return s / (double)bk.nq;
 }
 
 // x^p by repeated multiplication (universal.jl:60-62: `x .^ n` with integer n), same rounding as the plain loop

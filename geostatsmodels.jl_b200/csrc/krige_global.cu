@@ -226,7 +226,7 @@ constexpr int QSTAGES = 3;
 constexpr int QTHREADS = 256;
 
 __global__ void __launch_bounds__(256)
-global_r_kernel(GlobalDev gd, VarioDev v, TargetsDev tg, long long t0, int mb, double* __restrict__ R,
+global_r_kernel(GlobalDev gd, VarioDev v, TargetsDev tg, BlockDev bk, long long t0, int mb, double* __restrict__ R,
                 double* __restrict__ dots) {
   // block: 64 targets x 128 samples; thread: target tid % 64, 32 samples of group tid / 64
   __shared__ double part[4][1 + GSM_MAX_DRIFT][64];
@@ -243,7 +243,7 @@ global_r_kernel(GlobalDev gd, VarioDev v, TargetsDev tg, long long t0, int mb, d
     double r = 0.0;
     if (s < gd.n && tlive) {
       const double dx = gd.px[s] - tx, dy = gd.py[s] - ty, dz = gd.pz[s] - tz;
-      r = gsm_cov_vec(v, dx, dy, dz);
+      r = bk.nq > 0 ? gsm_cov_block(v, bk, dx, dy, dz) : gsm_cov_vec(v, dx, dy, dz);
       for (int c = 0; c <= gd.ncon; ++c) acc[c] = fma(gd.D[(size_t)c * gd.np + s], r, acc[c]);
     }
     R[(size_t)s * mb + n] = r;
@@ -340,7 +340,7 @@ global_gemm_norm_kernel(const double* __restrict__ Linv, int np, const double* _
   if (tid < PT) uu[(size_t)ib * mb + cb * PT + tid] = (red[tid] + red[PT + tid]) + (red[2 * PT + tid] + red[3 * PT + tid]);
 }
 
-__global__ void global_finish_kernel(GlobalDev gd, VarioDev v, ModelDev m, TargetsDev tg, long long t0, int mb,
+__global__ void global_finish_kernel(GlobalDev gd, double c0, ModelDev m, TargetsDev tg, long long t0, int mb,
                                      const double* __restrict__ dots_part, const double* __restrict__ uu_part,
                                      double* __restrict__ out_mean, double* __restrict__ out_var) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,7 +353,7 @@ __global__ void global_finish_kernel(GlobalDev gd, VarioDev v, ModelDev m, Targe
     for (int c = 0; c <= ncon; ++c) dots[c] += dots_part[((size_t)ib * (1 + GSM_MAX_DRIFT) + c) * mb + n];
     if (out_var) usum += uu_part[(size_t)ib * mb + n];
   }
-  double mean = dots[0], var = v.sill - usum;
+  double mean = dots[0], var = c0 - usum;   // c0: covzero (krig.jl:295-301), the sill for a point target
   if (m.kind == GSM_KRIG_SIMPLE) {
     mean += m.mean;
   } else {
@@ -740,6 +740,7 @@ int gsm_global_krige_predict(gsm_fit* f, const gsm_targets* t, double* out_mean,
     for (int a = 0; a < f->ncon * f->ncon; ++a) gd.Ginv[a] = f->S[a];
     for (int a = 0; a < f->ncon; ++a) gd.hw[a] = f->h[a];
     const VarioDev vd = gsm_make_vario(f->vario);
+    GSM_CHECK(gsm_block_prepare(ctx, vd));
     ModelDev md{};
     md.kind = f->model.kind;
     md.mean = f->model.mean;
@@ -760,10 +761,10 @@ int gsm_global_krige_predict(gsm_fit* f, const gsm_targets* t, double* out_mean,
       const size_t smem = (size_t)QSTAGES * QK * (QLDA + QLDB) * sizeof(double);
       GSM_CUDA(ctx, cudaFuncSetAttribute(global_gemm_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       for (long long t0 = 0; t0 < count; t0 += mb) {
-        global_r_kernel<<<dim3((unsigned)ncb, (unsigned)nib), 256, 0, st>>>(gd, vd, td, t0, (int)mb, Rb, dots);
+        global_r_kernel<<<dim3((unsigned)ncb, (unsigned)nib), 256, 0, st>>>(gd, vd, td, ctx->block_cur, t0, (int)mb, Rb, dots);
         if (dvar)
           global_gemm_norm_kernel<<<(unsigned)(ncb * nib), QTHREADS, smem, st>>>(gd.Linv, np, Rb, (int)mb, ncb, uu);
-        global_finish_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(gd, vd, md, td, t0, (int)mb, dots, uu, dmean, dvar);
+        global_finish_kernel<<<(unsigned)((mb + 127) / 128), 128, 0, st>>>(gd, ctx->block_cur.c0, md, td, t0, (int)mb, dots, uu, dmean, dvar);
         ctx->tim.launches += dvar ? 3 : 2;
       }
       GSM_CUDA(ctx, cudaGetLastError());

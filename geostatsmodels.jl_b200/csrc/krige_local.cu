@@ -44,7 +44,7 @@ struct WarpSmem {
 // minimum-norm solution; where it is not, the system is flagged singular.
 template <int NCON, bool MISS>
 __global__ void __launch_bounds__(LK_THREADS, 4)
-local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int minn, int centered,
+local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, BlockDev bk, int k, int minn, int centered,
                    const int* __restrict__ pos, const int* __restrict__ cnt, double* __restrict__ out_mean,
                    double* __restrict__ out_var, unsigned char* __restrict__ out_status) {
   __shared__ __align__(16) WarpSmem smem[LK_WARPS];
@@ -115,7 +115,7 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   {
     const double dx = r.x - tx, dy = r.y - ty, dz = r.z - tz;
     d2t = dx * dx + dy * dy + dz * dz;
-    rhs[0] = live ? gsm_cov_vec(v, dx, dy, dz) : 0.0;
+    rhs[0] = live ? (bk.nq > 0 ? gsm_cov_block(v, bk, dx, dy, dz) : gsm_cov_vec(v, dx, dy, dz)) : 0.0;
     rhs[1] = live ? (NCON == 0 ? r.w - m.mean : r.w) : 0.0;
   }
   double f0[NCON > 0 ? NCON : 1];
@@ -175,7 +175,7 @@ local_krige_kernel(BinsDev b, VarioDev v, ModelDev m, TargetsDev tg, int k, int 
   const double uu = gsm_warp_sum(rhs[0] * rhs[0]);
   const double wu = gsm_warp_sum(rhs[1] * rhs[0]);
   double mean, var;
-  const double c0 = v.sill;  // covzero for a point target: sill - gamma(0)  (krig.jl:295-301)
+  const double c0 = bk.c0;  // covzero (krig.jl:295-301): sill - gamma(0) = sill for a point target
   if (NCON == 0) {
     mean = m.mean + wu;
     var = c0 - uu;
@@ -333,7 +333,7 @@ template <int NCON, bool MISS = false>
 int launch(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k, int minn, int centered,
            const int* pos, const int* cnt, double* mean, double* var, unsigned char* status) {
   long long blocks = (tg.count + LK_WARPS - 1) / LK_WARPS;
-  local_krige_kernel<NCON, MISS><<<(unsigned)blocks, LK_THREADS, 0, ctx->stream>>>(ctx->bins, v, m, tg, k, minn, centered,
+  local_krige_kernel<NCON, MISS><<<(unsigned)blocks, LK_THREADS, 0, ctx->stream>>>(ctx->bins, v, m, tg, ctx->block_cur, k, minn, centered,
                                                                             pos, cnt, mean, var, status);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());
@@ -373,6 +373,10 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool nonconst = false;
   for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
   const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
+  if (ctx->block_cur.nq > 0 && k > 32) {
+    gsm_set_error(ctx, "change of support is claimed for maxneighbors <= 32 only");
+    return GSM_ERR_UNSUPPORTED;
+  }
   if (ctx->n_missing > 0) {
     // samples with a missing value (NaN): the kernel that restates lhsmissings! / rhsmissings! / the SVD solve
     if (k > 32) {
@@ -408,7 +412,7 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool patches = tg.kind == GSM_TARGETS_GRID && tg.dim >= 2 && tg.dims[1] > 1;
   if (patches) {
     // Sharing pays when the neighbourhood is wide compared with a patch: radius of the k nearest samples in units
-    // of the target spacing, from the mean sample density of the bins.  Measured crossover (tools/ab_dense.py,
+    // of the target spacing, from the mean sample density of the bins.  Measured crossover (tools/ab_density_sweep.py,
     // tools/run_configs.py): ~5 cells in 2-D (4 x 2 patches), ~3 in 3-D (2 x 2 x 2); below it the pools overflow
     // or share little and the per-system pipelined kernel is faster.
     const BinsDev& bn = ctx->bins;
@@ -424,6 +428,7 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   }
   int impl = ctx->opt_local_impl;
   if (v.general) impl = GSM_IMPL_SIMT;   // composite / anisotropic / newer families: the general covariance function
+  if (ctx->block_cur.nq > 0) impl = GSM_IMPL_SIMT;   // block targets: right-hand sides averaged over the block's points
   if (impl == GSM_IMPL_AUTO) impl = (k > 8 && patches) ? GSM_IMPL_SHR : GSM_IMPL_PIPE;
   if (impl == GSM_IMPL_PATCH || impl == GSM_IMPL_PATCH2) {
     int rc = gsm_launch_local_krige_patch(ctx, v, m, ncon, centered, tg, k, minneighbors, d_pos, d_cnt, d_mean, d_var,

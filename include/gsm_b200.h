@@ -170,6 +170,18 @@ GSM_API int gsm_synchronize(gsm_ctx* ctx);
  * maxneighbors <= 32), "shr_smax" = 0..3, "bin_occupancy" = samples per search cell (next gsm_set_samples). */
 GSM_API int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value);
 
+/* Change of support (fitpredict `point=false`, /root/reference/src/models.jl:114-115,136,205): every target of the
+ * following gsm_local_krige (maxneighbors <= 32) / gsm_global_krige_predict calls stands for the nq points
+ * centroid + offsets[q] (equal weights; offsets nq x dim, AoS, in the coordinates of the samples, i.e. already
+ * multiplied by the scale factor).  The right-hand side becomes the mean covariance between a sample and those points
+ * (pairwise! on [g0] + rhsbanded!, krig.jl:342-378), covzero the mean covariance over all nq^2 pairs of them
+ * (krig.jl:295-301); the search centre and the drift functions stay at the centroid (models.jl:164,
+ * universal.jl:125-126), and IDW / NN only ever see the centroid (idw.jl:82, nn.jl:57-66), so they ignore this.
+ * Which points represent a cell is the caller's rule (upstream it lives in GeoStatsFunctions, not in the reference
+ * tree); congruent grid cells need one offset table.  nq = 0 returns to point support. */
+#define GSM_MAX_BLOCK_POINTS 512
+GSM_API int gsm_set_block_support(gsm_ctx* ctx, const double* offsets, int dim, int nq);
+
 /* Pinned host buffers so outputs DMA straight into caller-owned memory (Julia: unsafe_wrap). */
 GSM_API int gsm_host_alloc(void** out, int64_t bytes);
 GSM_API int gsm_host_free(void* p);

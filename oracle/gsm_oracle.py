@@ -270,10 +270,16 @@ class KrigingSystem:
             LHS[self.miss, :n] = 0.0
         return LHS
 
-    def rhs(self, x0: np.ndarray) -> np.ndarray:  # krig.jl:342-361
+    def rhs(self, x0: np.ndarray, block=None) -> np.ndarray:  # krig.jl:342-361
+        """block: (nq, dim) offsets of the points that stand for a target with volume support; pairwise!(RHS, fun, dom,
+        [g0]) then evaluates fun(point, geometry) = the mean over those points (GeoStatsFunctions), rhsbanded! turns
+        it into sill - mean gamma = mean covariance; the drift functions see the centroid (universal.jl:125-126)."""
         model, n, m = self.model, self.n, self.m
         r = np.zeros(m)
-        r[:n] = cov_points(model.vario, self.X, x0[None, :])[:, 0]
+        if block is None:
+            r[:n] = cov_points(model.vario, self.X, x0[None, :])[:, 0]
+        else:
+            r[:n] = cov_points(model.vario, self.X, x0[None, :] + np.asarray(block, dtype=np.float64)).mean(axis=1)
         if model.kind == OK:
             r[n] = 1.0
         elif model.kind == UK:
@@ -282,8 +288,8 @@ class KrigingSystem:
             r[self.miss] = 0.0
         return r
 
-    def weights(self, x0: np.ndarray):
-        r = self.rhs(np.asarray(x0, dtype=np.float64))
+    def weights(self, x0: np.ndarray, block=None):
+        r = self.rhs(np.asarray(x0, dtype=np.float64), block)
         if len(self.miss) == 0:
             w, info = lapack.dsytrs(self._ldu, self._ipiv, r, lower=0)  # FHS \ RHS
         else:
@@ -294,9 +300,9 @@ class KrigingSystem:
             w = self._Vt[:kk].T @ ((self._U[:, :kk].T @ r) / S[:kk])
         return w, r
 
-    def predict(self, x0):
+    def predict(self, x0, block=None):
         """(mean, variance) at x0: krigmean (krig.jl:245-258 / simple.jl:55-69), predictvar (264-293)."""
-        w, r = self.weights(x0)
+        w, r = self.weights(x0, block)
         n = self.n
         lam, nu = w[:n], w[n:]
         zz = np.where(np.isnan(self.z), 0.0, self.z)            # lambda (.) missing = 0 (krig.jl:261-262)
@@ -306,6 +312,9 @@ class KrigingSystem:
         else:
             mu = float(np.sum(lam_v * zz))
         c0 = self.model.vario.total_sill  # covzero for a point: sill - gamma(0) (krig.jl:295-301)
+        if block is not None:             # sill - fun(g0, g0): the mean over all pairs of the block's points
+            B = np.asarray(block, dtype=np.float64)
+            c0 = float(cov_points(self.model.vario, B, B).mean())
         var = c0 - float(r[:n] @ lam) - float(r[n:] @ nu) + VAR_EPS
         return mu, var
 
@@ -484,6 +493,24 @@ def nn_predict(X: np.ndarray, z: np.ndarray, x0: np.ndarray) -> float:
     return float(z[np.lexsort((np.arange(X.shape[0]), d2))[0]])
 
 
+def block_offsets(sides, vrange: float) -> np.ndarray:
+    """The points that stand for an axis-aligned cell with the given side lengths, relative to its centroid
+    [RECALLED: GeoStatsFunctions is not in the reference tree]: spacing s = min(range, shortest side) / 3,
+    n_d = ceil(side_d / s) points per dimension, regular lattice including both ends (Meshes RegularSampling on a
+    non-periodic parametrisation), first coordinate fastest.  Nothing in the reference's tests pins the rule itself
+    (test/krig.jl:221-242 only asserts var >= 0): parity unpinned for the rule, pinned for the arithmetic given the
+    points."""
+    sides = [abs(float(s_)) for s_ in sides]
+    short = min([s_ for s_ in sides if s_ > 0] or [1.0])
+    s = (min(vrange, short) if (vrange > 0 and np.isfinite(vrange)) else short) / 3.0
+    axes = []
+    for side in sides:
+        n = max(int(np.ceil(side / s - 1e-9)), 1) if side > 0 else 1
+        axes.append([(-0.5 + i / (n - 1)) * side for i in range(n)] if n > 1 else [0.0])
+    pts = [tuple(reversed(t_)) for t_ in itertools.product(*reversed(axes))]   # last axis outermost
+    return np.asarray(pts, dtype=np.float64)
+
+
 def _targets(dom, first=0, count=None) -> np.ndarray:
     if isinstance(dom, Grid):
         return dom.centroids(first, count)
@@ -497,7 +524,7 @@ def _dom_absmax(dom) -> float:
 
 
 def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, maxneighbors=10,
-               neighborhood=None, first=0, count=None, return_neighbors=False):
+               neighborhood=None, first=0, count=None, return_neighbors=False, block_offsets=None):
     """Returns (mean[M], var[M] or None, status[M] uint8, [nbr list]).  status: 0 ok, 1 missing
     (fewer than minneighbors found, models.jl:178-181), 2 factorisation failed."""
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -511,6 +538,11 @@ def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, 
     else:
         sT = _targets(np.asarray(dom, dtype=np.float64) * alpha, first, count)
     srad = None if neighborhood is None else alpha * float(neighborhood)
+    # point=false (models.jl:114-115,136): block_offsets (nq, dim) are the points of a cell relative to its centroid;
+    # only Kriging looks beyond the centroid (idw.jl:82, nn.jl:57-66)
+    sblock = None
+    if block_offsets is not None and isinstance(model, KrigingModel):
+        sblock = np.asarray(block_offsets, dtype=np.float64) * alpha
     M = sT.shape[0]
     mean = np.full(M, np.nan)
     var = np.full(M, np.nan) if prob else None
@@ -529,7 +561,7 @@ def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, 
             if len(idx) < minneighbors:
                 status[j] = 1
                 continue
-            mean[j], v, ok = _predict_one(smodel, sX[idx], z[idx], sT[j])
+            mean[j], v, ok = _predict_one(smodel, sX[idx], z[idx], sT[j], sblock)
             if prob:
                 var[j] = v
             if not ok:
@@ -538,7 +570,7 @@ def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, 
         if isinstance(smodel, KrigingModel):
             ks = KrigingSystem(smodel, sX, z)
             for j in range(M):
-                mean[j], v = ks.predict(sT[j])
+                mean[j], v = ks.predict(sT[j], sblock)
                 if prob:
                     var[j] = v
             if not ks.status():
@@ -554,11 +586,11 @@ def fitpredict(model, X, z, dom, *, prob=False, neighbors=True, minneighbors=1, 
     return mean, var, status
 
 
-def _predict_one(smodel, Xn, zn, x0):
+def _predict_one(smodel, Xn, zn, x0, block=None):
     if isinstance(smodel, NNModel):
         return nn_predict(Xn, zn, x0), 0.0, True
     if isinstance(smodel, KrigingModel):
         ks = KrigingSystem(smodel, Xn, zn)
-        mu, v = ks.predict(x0)
+        mu, v = ks.predict(x0, block)
         return mu, v, ks.status()
     return idw_predict(Xn, zn, x0, smodel.exponent), 0.0, True

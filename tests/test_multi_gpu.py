@@ -112,3 +112,25 @@ def test_multi_and_option_error_paths(gsm):
         got = gsm.fitpredict(model, tab, grid, maxneighbors=32, prob=True, ctx=c).z
         assert np.allclose(got.mu, ref.mu, rtol=1e-11, atol=1e-12) and np.allclose(got.sigma, ref.sigma, rtol=1e-11, atol=1e-12), impl
     c.close()
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_multi_change_of_support(gsm, ndev):
+    """point=false through the multi-GPU handle: the block table goes to every device's context."""
+    if _ndev() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    rng = np.random.default_rng(93)
+    dims = (96, 64)
+    X = rng.uniform(0, 1, size=(5000, 2)) * np.array(dims, dtype=float)
+    z = np.sin(X[:, 0] / 9) + 0.1 * rng.standard_normal(5000)
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    grid = gsm.CartesianGrid(*dims)
+    gm = gsm.OrdinaryKriging(gsm.SphericalVariogram(range=12.0, nugget=0.1))
+    for kw in (dict(maxneighbors=16), dict(neighbors=False)):
+        data = tab if kw.get("neighbors", True) else gsm.georef({"z": z[:600]}, gsm.PointSet(X[:600]))
+        one = gsm.fitpredict(gm, data, grid, point=False, prob=True, **kw).z
+        many = gsm.fitpredict(gm, data, grid, point=False, prob=True, devices=list(range(ndev)), **kw).z
+        pt = gsm.fitpredict(gm, data, grid, point=True, prob=True, devices=list(range(ndev)), **kw).z
+        assert np.array_equal(np.asarray(one.mu), np.asarray(many.mu))
+        assert np.array_equal(np.asarray(one.sigma), np.asarray(many.sigma))
+        assert np.abs(np.asarray(pt.sigma) - np.asarray(many.sigma)).max() > 1e-6   # (and the table was cleared again)
