@@ -696,8 +696,6 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     # only look at centroids (idw.jl:82, nn.jl); a Kriging model on a grid averages the right-hand side over the cell
     block = None
     if not point and isinstance(dom, CartesianGrid) and isinstance(model, _KrigingModel):
-        if neighbors and _clamp_max(maxneighbors, len(_pointset_of(data.domain))) > 32:
-            raise NotImplementedError("change of support is claimed for maxneighbors <= 32")
         block = block_points(dom, model._range()) if block_offsets is None else np.asarray(block_offsets, dtype=np.float64)
         if block.ndim != 2 or block.shape[1] != dom.dim or len(block) < 1:
             raise ValueError("block_offsets must be (nq, dim) with nq >= 1")
@@ -732,6 +730,8 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         z = _values_of(data, names[0])
         X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
         nobs = len(z)
+    if block is not None and neighbors and _clamp_max(maxneighbors, nobs) > 32:
+        raise NotImplementedError("change of support is claimed for maxneighbors <= 32")
     if ctx is None and devices is not None and len(devices) > 1:
         ctx = multi_context(devices)
     ctx = ctx or default_context(device if devices is None else devices[0])

@@ -8,7 +8,8 @@
 # What it does: adds more-specific methods of `GeoStatsModels.fitpredictneigh` / `fitpredictfull`
 # (src/models.jl:131-234) for the signatures the GPU path claims -- Kriging (Simple / Ordinary / Universal
 # built by `(deg, dim)`, i.e. stock `Kriging(γ, deg, dim)`), IDW and NN with Euclidean distance, univariate
-# Float64 (or Union{Missing,Float64}) Cartesian PointSet data, CartesianGrid or PointSet targets, point support.
+# Float64 (or Union{Missing,Float64}) Cartesian PointSet data, CartesianGrid or PointSet targets, point support or
+# (Kriging on a CartesianGrid) volume support: `point=false` hands the library the points upstream integrates over.
 # Every other signature keeps dispatching to the untouched generic methods (that is dispatch, not a CPU
 # fallback inside the library).  `fitpredict` itself (models.jl:102-129) is unchanged, so `_pointsupport`,
 # `_scale` and the final `georef` run exactly as in the reference and the shim receives ALREADY SCALED
@@ -146,9 +147,32 @@ end
 
 column(dat) = Tables.getcolumn(Tables.columns(values(dat)), 1)
 claimed(dat, dom, point, distance) =
-  point && distance isa Euclidean && domain(dat) isa PointSet && dom isa Union{CartesianGrid,PointSet} &&
+  distance isa Euclidean && domain(dat) isa PointSet && dom isa Union{CartesianGrid,PointSet} &&
   length(Tables.columnnames(Tables.columns(values(dat)))) == 1 &&
   nonmissingtype(eltype(column(dat))) === Float64
+
+# Change of support (point=false, models.jl:114-115,136,205): the points GeoStatsFunctions integrates over for one
+# cell, relative to its centroid.  Every cell of a CartesianGrid is congruent, so one table serves the whole domain;
+# the elements of a PointSet are points anyway, and IDW / NN only look at centroids (idw.jl:82, nn.jl).  The sampling
+# rule stays upstream's own (`GeoStatsFunctions._sample`, an internal name [RECALLED]); without it the call is not claimed.
+function blocktable(γ, dom, point)
+  (point || !(dom isa CartesianGrid)) && return nothing
+  isdefined(GeoStatsFunctions, :_sample) || throw(Unsupported())
+  g = dom[1]
+  c = collect(ustrip.(to(centroid(g))))
+  B = reduce(hcat, [collect(ustrip.(to(p))) .- c for p in GeoStatsFunctions._sample(γ, g)])   # dim x nq == AoS
+  size(B, 2) <= 512 || throw(Unsupported())                  # GSM_MAX_BLOCK_POINTS
+  B
+end
+contexts(h) = h.multi ? [ccall((:gsm_multi_context, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), h.ptr, i - 1)
+                         for i in 1:ccall((:gsm_multi_device_count, LIB), Cint, (Ptr{Cvoid},), h.ptr)] : [h.ptr]
+function setblock!(h, B)
+  for c in contexts(h)
+    rc = B === nothing ? ccall((:gsm_set_block_support, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), c, C_NULL, 0, 0) :
+                         ccall((:gsm_set_block_support, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32), c, B, size(B, 1), size(B, 2))
+    check(h, rc)
+  end
+end
 
 # neighbour limits exactly like models.jl:144-150; the library takes up to MAXK neighbours
 clampmax(maxneighbors, nobs) = (maxneighbors > nobs || maxneighbors < 1) ? nobs : maxneighbors
@@ -192,7 +216,9 @@ function fitpredictneigh(model::Union{SimpleKriging,OrdinaryKriging,UniversalKri
   try
     h = handle()
     v = Ref(variogram(model.fun)); m = Ref(gsmmodel(model, embeddim(dom)))
-    setsamples!(h, dat)
+    B = blocktable(model.fun, dom, point)
+    (B === nothing || clampmax(maxneighbors, nrow(dat)) <= 32) || throw(Unsupported())
+    setsamples!(h, dat); setblock!(h, B)
     M = nelements(dom); var = first(Tables.columnnames(Tables.columns(values(dat))))
     mean = pinned(Float64, M); vari = prob ? pinned(Float64, M) : Float64[]; status = pinned(UInt8, M)
     tg, keep = targets(dom)
@@ -208,6 +234,7 @@ function fitpredictneigh(model::Union{SimpleKriging,OrdinaryKriging,UniversalKri
           h.ptr, v, m, Ref(tg), o, mean, prob ? pointer(vari) : C_NULL, status, C_NULL))
       end
     end
+    B === nothing || setblock!(h, nothing)
     col = columnof(mean, vari, status, prob, summary(h))
     return (; var => col) |> Tables.materializer(values(dat))
   catch e
@@ -223,7 +250,8 @@ function fitpredictfull(model::Union{SimpleKriging,OrdinaryKriging,UniversalKrig
   try
     h = handle()
     v = Ref(variogram(model.fun)); m = Ref(gsmmodel(model, embeddim(dom)))
-    setsamples!(h, dat)
+    B = blocktable(model.fun, dom, point)
+    setsamples!(h, dat); setblock!(h, B)
     M = nelements(dom); var = first(Tables.columnnames(Tables.columns(values(dat))))
     mean = pinned(Float64, M); vari = prob ? pinned(Float64, M) : Float64[]
     tg, keep = targets(dom)
@@ -242,6 +270,7 @@ function fitpredictfull(model::Union{SimpleKriging,OrdinaryKriging,UniversalKrig
         ccall((:gsm_global_krige_free, LIB), Cint, (Ptr{Cvoid},), fit[])
       end
     end
+    B === nothing || setblock!(h, nothing)
     col = prob ? Normal.(mean, vari) : mean
     return (; var => col) |> Tables.materializer(values(dat))
   catch e
