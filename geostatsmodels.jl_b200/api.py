@@ -730,8 +730,6 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         z = _values_of(data, names[0])
         X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
         nobs = len(z)
-    if block is not None and neighbors and _clamp_max(maxneighbors, nobs) > 32:
-        raise NotImplementedError("change of support is claimed for maxneighbors <= 32")
     if ctx is None and devices is not None and len(devices) > 1:
         ctx = multi_context(devices)
     ctx = ctx or default_context(device if devices is None else devices[0])

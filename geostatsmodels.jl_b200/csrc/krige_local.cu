@@ -373,10 +373,6 @@ int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m_in
   bool nonconst = false;
   for (int a = 0; a < m.ndrift; ++a) nonconst |= (m.exps[a][0] | m.exps[a][1] | m.exps[a][2]) != 0;
   const int centered = (ncon > 0 && nonconst && is_lower_set(m)) ? 1 : 0;
-  if (ctx->block_cur.nq > 0 && k > 32) {
-    gsm_set_error(ctx, "change of support is claimed for maxneighbors <= 32 only");
-    return GSM_ERR_UNSUPPORTED;
-  }
   if (ctx->n_missing > 0) {
     // samples with a missing value (NaN): the kernel that restates lhsmissings! / rhsmissings! / the SVD solve
     if (k > 32) {

@@ -108,7 +108,8 @@ template <int NRB>
 __global__ void __launch_bounds__(MW * 64)
 local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant__ VarioDev v,
                        const __grid_constant__ ModelDev m, const __grid_constant__ gsm_cov::CovFast cf, int ncon,
-                       int centered, const __grid_constant__ TargetsDev tg, int k, int minn,
+                       int centered, const __grid_constant__ TargetsDev tg, const __grid_constant__ BlockDev bk, int k,
+                       int minn,
                        const int* __restrict__ pos,
                        const int* __restrict__ cnt, double* __restrict__ out_mean, double* __restrict__ out_var,
                        unsigned char* __restrict__ out_status) {
@@ -242,7 +243,8 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
           if (q < nr && c < n) {
             if (q == 0) {
               const double dx = S.px[c] - tx, dy = S.py[c] - ty, dz = S.pz[c] - tz;
-              val = v.general ? gsm_cov_general(v, dx, dy, dz) : gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
+              if (bk.nq > 0) val = gsm_cov_block(v, bk, dx, dy, dz);   // change of support: mean over the block's points
+              else val = v.general ? gsm_cov_general(v, dx, dy, dz) : gsm_cov::cov_fast(cf, fma(dz, dz, fma(dy, dy, dx * dx)));
             } else if (q == 1) {
               val = (m.kind == GSM_KRIG_SIMPLE) ? S.pv[c] - m.mean : S.pv[c];
             } else {
@@ -341,7 +343,7 @@ local_krige_mid_kernel(const __grid_constant__ BinsDev b, const __grid_constant_
         return -S.G[br * (br + 1) / 2 + bc][(a & 7) * 8 + (bb & 7)];
       };
       const double uu = Gm(0, 0), wu = Gm(1, 0);
-      const double c0 = v.sill;
+      const double c0 = bk.c0;   // covzero (krig.jl:295-301): the sill for a point target
       double mean, var;
       if (ncon == 0) {
         mean = m.mean + wu;
@@ -401,7 +403,7 @@ int launch_mid(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, int ncon, int
   const int per_sm = (int)std::max<size_t>(1, (227 * 1024) / (smem + 1024));
   const long long want = (tg.count + MW - 1) / MW;
   const int blocks = (int)std::min<long long>(want, 148LL * per_sm);
-  kern<<<blocks, MW * 64, smem, ctx->stream>>>(ctx->bins, v, m, gsm_cov::make_cov(v), ncon, centered, tg, k, minn, pos, cnt,
+  kern<<<blocks, MW * 64, smem, ctx->stream>>>(ctx->bins, v, m, gsm_cov::make_cov(v), ncon, centered, tg, ctx->block_cur, k, minn, pos, cnt,
                                                mean, var, status);
   ctx->tim.launches++;
   GSM_CUDA(ctx, cudaGetLastError());

@@ -171,7 +171,7 @@ GSM_API int gsm_synchronize(gsm_ctx* ctx);
 GSM_API int gsm_set_option(gsm_ctx* ctx, const char* key, const char* value);
 
 /* Change of support (fitpredict `point=false`, /root/reference/src/models.jl:114-115,136,205): every target of the
- * following gsm_local_krige (maxneighbors <= 32) / gsm_global_krige_predict calls stands for the nq points
+ * following gsm_local_krige / gsm_global_krige_predict calls stands for the nq points
  * centroid + offsets[q] (equal weights; offsets nq x dim, AoS, in the coordinates of the samples, i.e. already
  * multiplied by the scale factor).  The right-hand side becomes the mean covariance between a sample and those points
  * (pairwise! on [g0] + rhsbanded!, krig.jl:342-378), covzero the mean covariance over all nq^2 pairs of them

@@ -217,7 +217,6 @@ function fitpredictneigh(model::Union{SimpleKriging,OrdinaryKriging,UniversalKri
     h = handle()
     v = Ref(variogram(model.fun)); m = Ref(gsmmodel(model, embeddim(dom)))
     B = blocktable(model.fun, dom, point)
-    (B === nothing || clampmax(maxneighbors, nrow(dat)) <= 32) || throw(Unsupported())
     setsamples!(h, dat); setblock!(h, B)
     M = nelements(dom); var = first(Tables.columnnames(Tables.columns(values(dat))))
     mean = pinned(Float64, M); vari = prob ? pinned(Float64, M) : Float64[]; status = pinned(UInt8, M)

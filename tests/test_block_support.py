@@ -101,6 +101,7 @@ def test_local_block_kriging_against_oracle(gsm, oracle, dim):
         blk = gsm.block_points(grid, gv.range)
         for gm, om, kw in ((gsm.SimpleKriging(gv, 0.2), o.simple_kriging(ov, 0.2), dict(maxneighbors=12)),
                            (gsm.OrdinaryKriging(gv), o.ordinary_kriging(ov), dict(maxneighbors=32)),
+                           (gsm.OrdinaryKriging(gv), o.ordinary_kriging(ov), dict(maxneighbors=44)),
                            (gsm.UniversalKriging(gv, 1, dim), o.universal_kriging(ov, 1, dim), dict(maxneighbors=20, minneighbors=3,
                                                                                                   neighborhood=9.0))):
             mu, var, st = o.fitpredict(om, X, z, og, prob=True, block_offsets=blk, **kw)
@@ -204,9 +205,7 @@ def test_block_support_boundaries(gsm, oracle):
     finally:
         ctx.set_option("local_impl", "auto")
     assert np.allclose(a.mu, b.mu, rtol=1e-12, atol=1e-13) and np.allclose(a.sigma, b.sigma, rtol=1e-12, atol=1e-13)
-    # claimed for maxneighbors <= 32; too many points per cell is refused, not truncated
-    with pytest.raises(NotImplementedError):
-        gsm.fitpredict(gsm.OrdinaryKriging(gv), tab, grid, point=False, maxneighbors=48)
+    # too many points per cell is refused, not truncated
     with pytest.raises(NotImplementedError):
         gsm.fitpredict(gsm.OrdinaryKriging(gsm.SphericalVariogram(range=0.05)), tab, grid, point=False, maxneighbors=8)
     with pytest.raises(gsm.GsmError):
