@@ -25,7 +25,7 @@ __all__ = [
     "SineHoleVariogram", "CircularVariogram", "NuggetEffect", "CompositeVariogram", "PointSet", "CartesianGrid", "GeoTable",
     "georef", "IDW", "NN", "SimpleKriging", "OrdinaryKriging", "UniversalKriging", "Kriging", "Normal", "fit",
     "predict", "predictprob", "status", "fitpredict", "default_context", "multi_context", "set_default_device", "Dirac",
-    "Box", "Quadrangle", "block_points",
+    "Box", "Quadrangle", "block_points", "MvNormal",
 ]
 
 
@@ -331,6 +331,28 @@ class Normal:
         return self.mu
 
 
+class MvNormal:
+    """MvNormal(mu, Sigma): the joint predictive distribution `predictprob(fitted, vars, g)` returns for several
+    variables (krig.jl:231-237); `var()` is the diagonal, as Distributions.var sees it."""
+
+    def __init__(self, mu, Sigma):
+        self.mu = np.asarray(mu, dtype=np.float64)
+        self.Sigma = np.asarray(Sigma, dtype=np.float64)
+        np.linalg.cholesky(self.Sigma)           # PosDefException of MvNormal(mu, Sigma), krig.jl:236
+
+    def mean(self):
+        return self.mu
+
+    def var(self):
+        return np.diag(self.Sigma).copy()
+
+    def cov(self):
+        return self.Sigma
+
+    def __repr__(self):
+        return f"MvNormal(mu={self.mu!r}, Sigma={self.Sigma!r})"
+
+
 # ---------------------------------------------------------------------------------------------
 # models
 # ---------------------------------------------------------------------------------------------
@@ -545,9 +567,32 @@ class FittedIDW:
         self.model, self.data, self._ctx, self._alpha = model, data, ctx, alpha
 
 
+class FittedCoKriging:
+    """fit(model, geotable) for a cokriging model with the proportional function B * gamma0 and isotopic data: the
+    reference's interleaved system (krig.jl:88-179 with nvar > 1) decouples into one univariate system per variable
+    (DESIGN.md 7), fitted on demand for the column a `vars` tuple binds to that variable (krig.jl:245-258)."""
+
+    def __init__(self, model, data, device):
+        self.model, self.data, self._device = model, data, device
+        self._fits = {}
+        for p, name in enumerate(data.names()):
+            self._fit_of(p, name)
+
+    def _fit_of(self, p, name):
+        if (p, name) not in self._fits:
+            one = GeoTable({name: self.data.table[name]}, self.data.domain)
+            self._fits[(p, name)] = fit(_marginal_model(self.model, p), one, device=self._device)
+        return self._fits[(p, name)]
+
+
 def fit(model, data: GeoTable, *, device=None, _alpha=1.0):
     """fit(model, geotable) (models.jl:38; krig.jl:58-75; idw.jl:43-49)."""
     _checkcompat(model, data)
+    if _nvariables(model) > 1:
+        for name in data.names():
+            if np.isnan(_values_of(data, name)).any():
+                raise NotImplementedError("cokriging with missing values (heterotopic data) is not claimed by the GPU path")
+        return FittedCoKriging(model, data, device)
     ctx = _lib.Context(_DEFAULT_DEVICE if device is None else device)  # a fitted model owns its samples
     X = _pointset_of(data.domain) * _alpha if _alpha != 1.0 else _pointset_of(data.domain)
     var = data.names()[0]
@@ -566,6 +611,8 @@ def status(fitted) -> bool:
     """status(fitted) (krig.jl:49-52; idw.jl:36)."""
     if isinstance(fitted, FittedIDW):
         return True
+    if isinstance(fitted, FittedCoKriging):
+        return all(f._gfit.status() for f in fitted._fits.values())
     return fitted._gfit.status()
 
 
@@ -611,8 +658,33 @@ def _krige_at(fitted, t, block, want_var):
             fitted._ctx.set_block_support(None)
 
 
+def _co_vars(fitted, var):
+    """the columns bound to the variables of a cokriging model: krigmean indexes vars[p] for p in 1:nvar (krig.jl:250-256)"""
+    names = (var,) if isinstance(var, str) else tuple(var)
+    if len(names) != _nvariables(fitted.model):
+        raise ValueError(f"{len(names)} variable(s) requested from a {_nvariables(fitted.model)}-variate Kriging model")
+    for nm in names:
+        if nm not in fitted.data.names():
+            raise KeyError(nm)
+    return names
+
+
+def _co_predict(fitted, var, g, want_var):
+    names = _co_vars(fitted, var)
+    mu, va = [], []
+    for p, nm in enumerate(names):
+        f = fitted._fit_of(p, nm)
+        t, block = _target_of(f, g)
+        m_, v_ = _krige_at(f, t, block, want_var)
+        mu.append(float(m_[0]))
+        va.append(float(v_[0]) if want_var else 0.0)
+    return np.array(mu), np.array(va)
+
+
 def predict(fitted, var, g):
     """predict(fitted, var, g) (krig.jl:215-219; idw.jl:55); g: a point or a Box (change of support)."""
+    if isinstance(fitted, FittedCoKriging):
+        return list(_co_predict(fitted, var, g, False)[0])
     _, scalar = _check_vars(fitted, var)
     t, block = _target_of(fitted, g)
     if isinstance(fitted, FittedIDW):
@@ -624,6 +696,15 @@ def predict(fitted, var, g):
 
 def predictprob(fitted, var, g):
     """predictprob(fitted, var, g): Normal(mu, sqrt(var)) for Kriging (krig.jl:223-229)."""
+    if isinstance(fitted, FittedCoKriging):
+        # Sigma = B sigma0^2 + 1e-10 I (krig.jl:264-293 for B * gamma0): every entry scales the base variance; the
+        # diagonal is each variable's own solve, the off-diagonal entries take sigma0^2 from the first variable
+        mu, va = _co_predict(fitted, var, g, True)
+        B = fitted.model.fun.B
+        s0 = (va[0] - 1e-10) / B[0, 0]
+        Sigma = B * s0 + 1e-10 * np.eye(len(mu))
+        Sigma[np.diag_indices(len(mu))] = va
+        return MvNormal(mu, Sigma)
     _, scalar = _check_vars(fitted, var)
     t, block = _target_of(fitted, g)
     if isinstance(fitted, FittedIDW):

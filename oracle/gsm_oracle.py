@@ -354,6 +354,11 @@ class CoKrigingSystem:
 
     def predict(self, x0):
         """(means[nvar], variances[nvar]) at x0: diag of Sigma + 1e-10 I as `var(MvNormal)` sees it"""
+        mu, Sigma = self.predict_full(x0)
+        return mu, np.diag(Sigma).copy()
+
+    def predict_full(self, x0):
+        """(means[nvar], Sigma[nvar, nvar]) at x0: the arguments of MvNormal(mu, Sigma) (krig.jl:231-237, 264-293)"""
         x0 = np.asarray(x0, dtype=np.float64)
         nv, n = self.nv, self.n
         g = variogram(self.vario, pairdist(self.X, x0[None, :])[:, 0])
@@ -380,7 +385,7 @@ class CoKrigingSystem:
                 acc += float(np.sum(lam[p_::nv, j] * zp))
             mu[j] = acc + (self.mean[j] if self.kind == SK else 0.0)
         Sigma = S - R[:self.nfun].T @ lam - R[self.nfun:].T @ nu + VAR_EPS * np.eye(nv)
-        return mu, np.diag(Sigma).copy()
+        return mu, Sigma
 
 
 # ----------------------------------------------------------------------------------------------

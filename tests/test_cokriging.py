@@ -73,3 +73,41 @@ def test_cokriging_gpu_matches_full_system(gsm, oracle):
                 assert abs(col.sigma[j] - var[p_]) <= 1e-9 * max(1.0, abs(var[p_]))
     with pytest.raises(ValueError):
         gsm.fitpredict(gsm.OrdinaryKriging(fun), gsm.georef({"a": Z[:, 0]}, gsm.PointSet(X)), gsm.PointSet(P))
+
+
+@pytest.mark.gpu
+def test_cokriging_fit_predictprob_reference_testset(gsm, oracle):
+    """test/krig.jl:348-395 through fit / predict / predictprob on the CUDA path (MvNormal over the three variables),
+    with the full covariance matrix checked against the reference's interleaved system restated by the oracle."""
+    o = oracle
+    P = np.array([[25.0, 25.0], [50.0, 75.0], [75.0, 50.0]])
+    Z = np.eye(3)
+    tab = gsm.georef({"a": Z[:, 0], "b": Z[:, 1], "c": Z[:, 2]}, gsm.PointSet(P))
+    fun = gsm.CoregionalizedVariogram(B3, gsm.SphericalVariogram(range=35.0))
+    g = o.Variogram(o.SPHERICAL, 1.0, 0.0, 35.0)
+    vars_ = ("a", "b", "c")
+    for gm, kind, kw in ((gsm.SimpleKriging(fun, [0.0, 0.0, 0.0]), o.SK, dict(mean=[0.0, 0.0, 0.0])),
+                         (gsm.OrdinaryKriging(fun), o.OK, {}),
+                         (gsm.UniversalKriging(fun, 1, 2), o.UK, dict(exps=o.monomial_exponents(1, 2))),
+                         (gsm.UniversalKriging(fun, exps=((0, 0),)), o.UK, dict(exps=((0, 0),)))):
+        f = gsm.fit(gm, tab)
+        assert gsm.status(f)
+        ks = o.CoKrigingSystem(kind, B3, g, P, Z, **kw)
+        for i in range(3):                                  # interpolation property
+            d = gsm.predictprob(f, vars_, P[i])
+            assert np.allclose(d.mean(), np.eye(3)[i], atol=1e-9) and np.allclose(d.var(), 0.0, atol=1e-8)
+        d = gsm.predictprob(f, vars_, (50.0, 50.0))
+        assert ((d.mean() >= 0) & (d.mean() <= 1)).all() and (d.var() >= 0).all()
+        mu, Sigma = ks.predict_full(np.array([50.0, 50.0]))
+        assert np.allclose(d.mean(), mu, rtol=1e-10, atol=1e-12)
+        assert np.allclose(d.cov(), Sigma, rtol=1e-9, atol=1e-12), np.abs(d.cov() - Sigma).max()
+        assert np.allclose(gsm.predict(f, vars_, (50.0, 50.0)), mu, rtol=1e-10, atol=1e-12)
+    f = gsm.fit(gsm.SimpleKriging(fun, [0.7, 0.2, 0.1]), tab)   # simple cokriging with non-zero means
+    for i in range(3):
+        assert np.allclose(gsm.predict(f, vars_, P[i]), np.eye(3)[i], atol=1e-9)
+    with pytest.raises(ValueError):
+        gsm.predict(f, ("a", "b"), P[0])
+    # the columns a `vars` tuple binds to the variables may be permuted (krigmean indexes vars[p], krig.jl:250-256)
+    ks = o.CoKrigingSystem(o.SK, B3, g, P, Z[:, [1, 0, 2]], mean=[0.7, 0.2, 0.1])
+    mu, _ = ks.predict_full(np.array([40.0, 60.0]))
+    assert np.allclose(gsm.predict(f, ("b", "a", "c"), (40.0, 60.0)), mu, rtol=1e-10, atol=1e-12)
