@@ -313,7 +313,9 @@ def _col_equal(a, b):
     return np.array_equal(np.ma.filled(a, np.nan), np.ma.filled(b, np.nan), equal_nan=True)
 
 
-def georef(table: dict, domain) -> GeoTable:
+def georef(table: dict, domain=None) -> GeoTable:
+    if domain is None:      # georef of plain vectors: a 1-D CartesianGrid with one cell per row (GeoTables)
+        domain = CartesianGrid(len(next(iter(table.values()))))
     if not isinstance(domain, (PointSet, CartesianGrid)):
         domain = PointSet(domain)
     return GeoTable(table, domain)
@@ -504,11 +506,34 @@ def _marginal_model(model, p):
     return UniversalKriging(f, exps=model.exps)
 
 
-def _pointset_of(domain) -> np.ndarray:
-    """_pointsupport (models.jl:265-270): centroids of the data domain."""
+def _pointset_of(domain, centroids_ok=False) -> np.ndarray:
+    """_pointsupport (models.jl:265-270): centroids of the data domain.  Data on a grid are claimed where the reference
+    itself only looks at centroids: IDW / NN (idw.jl:84, nn.jl:62), and every model once fitpredict(point=true) has
+    replaced the data geometries by their centroids."""
     if isinstance(domain, PointSet):
         return domain.coords
+    if isinstance(domain, CartesianGrid) and centroids_ok:
+        axes = [o + (np.arange(d) + 0.5) * sp for o, sp, d in zip(domain.origin, domain.spacing, domain.dims)]
+        mesh = np.meshgrid(*axes, indexing="ij")
+        return np.ascontiguousarray(np.stack([m_.ravel(order="F") for m_ in mesh], axis=1))
     raise NotImplementedError("GPU path claims PointSet data only")
+
+
+def _encode(col):
+    """(float64 codes with NaN for `missing`, categories or None): NN predicts any value type, e.g. strings
+    (test/nn.jl:3-10); values cross the C ABI as the index of their category."""
+    arr = col if np.ma.isMaskedArray(col) else np.asarray(col, dtype=object if isinstance(col, (list, tuple)) else None)
+    if np.ma.isMaskedArray(arr) or arr.dtype.kind in "fiub":
+        return np.ma.filled(np.ma.asarray(arr).astype(np.float64), np.nan), None
+    miss = np.array([v is None or (isinstance(v, float) and v != v) for v in arr])
+    if arr.dtype.kind == "O" and all(isinstance(v, (int, float)) and not isinstance(v, bool) for v in arr[~miss]):
+        out = np.full(len(arr), np.nan)
+        out[~miss] = [float(v) for v in arr[~miss]]
+        return out, None
+    cats, inv = np.unique(np.asarray([str(v) for v in arr[~miss]]), return_inverse=True)
+    out = np.full(len(arr), np.nan)
+    out[~miss] = inv
+    return out, cats
 
 
 def _values_of(data: "GeoTable", name) -> np.ndarray:
@@ -567,6 +592,14 @@ class FittedIDW:
         self.model, self.data, self._ctx, self._alpha = model, data, ctx, alpha
 
 
+class FittedNN:
+    """fit(NN(), geotable) (nn.jl:30-41): the samples whose value is not `missing` (nn.jl:47-54 takes the nearest of
+    those), values as category codes when they are not numbers."""
+
+    def __init__(self, model, data, ctx, cats, alpha=1.0):
+        self.model, self.data, self._ctx, self._cats, self._alpha = model, data, ctx, cats, alpha
+
+
 class FittedCoKriging:
     """fit(model, geotable) for a cokriging model with the proportional function B * gamma0 and isotopic data: the
     reference's interleaved system (krig.jl:88-179 with nvar > 1) decouples into one univariate system per variable
@@ -594,8 +627,17 @@ def fit(model, data: GeoTable, *, device=None, _alpha=1.0):
                 raise NotImplementedError("cokriging with missing values (heterotopic data) is not claimed by the GPU path")
         return FittedCoKriging(model, data, device)
     ctx = _lib.Context(_DEFAULT_DEVICE if device is None else device)  # a fitted model owns its samples
-    X = _pointset_of(data.domain) * _alpha if _alpha != 1.0 else _pointset_of(data.domain)
+    X = _pointset_of(data.domain, centroids_ok=isinstance(model, (IDW, NN)))
+    X = X * _alpha if _alpha != 1.0 else X
     var = data.names()[0]
+    if isinstance(model, NN):
+        z, cats = _encode(data.table[var])
+        keep = ~np.isnan(z)
+        if keep.any():
+            ctx.set_samples(X[keep], z[keep])
+        else:
+            ctx = None                                   # every value missing: predict answers `missing`
+        return FittedNN(model, data, ctx, cats, _alpha)
     z = _values_of(data, var)
     if isinstance(model, IDW):
         ctx.set_samples(X, z)
@@ -609,7 +651,7 @@ def fit(model, data: GeoTable, *, device=None, _alpha=1.0):
 
 def status(fitted) -> bool:
     """status(fitted) (krig.jl:49-52; idw.jl:36)."""
-    if isinstance(fitted, FittedIDW):
+    if isinstance(fitted, (FittedIDW, FittedNN)):
         return True
     if isinstance(fitted, FittedCoKriging):
         return all(f._gfit.status() for f in fitted._fits.values())
@@ -658,6 +700,16 @@ def _krige_at(fitted, t, block, want_var):
             fitted._ctx.set_block_support(None)
 
 
+def _nn_at(fitted, g):
+    """value of the nearest sample with a value (nn.jl:47-54); None stands for `missing`"""
+    if fitted._ctx is None:
+        return None
+    g = g.centroid() if isinstance(g, Box) else g
+    p = _as_point(g, fitted._ctx.dim) * fitted._alpha
+    code = float(fitted._ctx.nn(_lib.Context.point_targets(p))[0])
+    return code if fitted._cats is None else str(fitted._cats[int(code)])
+
+
 def _co_vars(fitted, var):
     """the columns bound to the variables of a cokriging model: krigmean indexes vars[p] for p in 1:nvar (krig.jl:250-256)"""
     names = (var,) if isinstance(var, str) else tuple(var)
@@ -685,6 +737,10 @@ def predict(fitted, var, g):
     """predict(fitted, var, g) (krig.jl:215-219; idw.jl:55); g: a point or a Box (change of support)."""
     if isinstance(fitted, FittedCoKriging):
         return list(_co_predict(fitted, var, g, False)[0])
+    if isinstance(fitted, FittedNN):
+        _, scalar = _check_vars(fitted, var)
+        v = _nn_at(fitted, g)
+        return v if scalar else [v]
     _, scalar = _check_vars(fitted, var)
     t, block = _target_of(fitted, g)
     if isinstance(fitted, FittedIDW):
@@ -696,6 +752,10 @@ def predict(fitted, var, g):
 
 def predictprob(fitted, var, g):
     """predictprob(fitted, var, g): Normal(mu, sqrt(var)) for Kriging (krig.jl:223-229)."""
+    if isinstance(fitted, FittedNN):
+        _, scalar = _check_vars(fitted, var)
+        d = Dirac(_nn_at(fitted, g))                     # predictprob = Dirac(predict) (nn.jl:45)
+        return d if scalar else [d]
     if isinstance(fitted, FittedCoKriging):
         # Sigma = B sigma0^2 + 1e-10 I (krig.jl:264-293 for B * gamma0): every entry scales the base variance; the
         # diagonal is each variable's own solve, the off-diagonal entries take sigma0^2 from the first variable
@@ -808,8 +868,22 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         names = data.names()
         if len(names) != 1:
             raise NotImplementedError("GPU path claims univariate tables only")
-        z = _values_of(data, names[0])
-        X = _pointset_of(data.domain)                      # _pointsupport, models.jl:115
+        cats = None
+        if isinstance(model, NN):
+            z, cats = _encode(data.table[names[0]])
+        else:
+            z = _values_of(data, names[0])
+        # _pointsupport (models.jl:115): centroids of the data geometries; with point=false the data keep their
+        # geometries, which only IDW / NN reduce to centroids themselves
+        X = _pointset_of(data.domain, centroids_ok=point or isinstance(model, (IDW, NN)))
+        if isinstance(model, NN) and not neighbors and np.isnan(z).any():
+            # fitpredictfull: the nearest sample WITH a value (nn.jl:47-54) = nearest of the samples that have one
+            # (the scale factor still comes from all samples, models.jl:286-291)
+            keep = ~np.isnan(z)
+            if not keep.any():
+                raise NotImplementedError("NN on a table without values is not claimed by the GPU path")
+            _nn_floor = float(np.abs(X).max())
+            X, z = np.ascontiguousarray(X[keep]), z[keep]
         nobs = len(z)
     if ctx is None and devices is not None and len(devices) > 1:
         ctx = multi_context(devices)
@@ -819,6 +893,8 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
     # caller's arrays are page-locked), absmax / alpha / `dat |> Scale(alpha)` / the NaN check run as kernels
     r = model._range()
     floor = max(1.0 if math.isinf(r) else r, dom._absmax())
+    if _device_samples is None and isinstance(model, NN) and not neighbors and len(z) != data.domain.nelements():
+        floor = max(floor, _nn_floor)
     kmodel = model
     if _device_samples is not None:
         alpha, nnan = ctx.set_samples_scaled(coords_d, values_d, floor, dim=sdim, n=nobs)
@@ -848,6 +924,10 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             minn = 1 if (minneighbors > kmax or minneighbors < 1) else minneighbors
             if (cnt < minn).any():
                 col = np.ma.masked_array(col, mask=cnt < minn)
+        if _device_samples is None and cats is not None:    # category codes back to the values
+            codes = np.ma.filled(col, 0).astype(np.int64)
+            vals = np.asarray(cats, dtype=object)[codes]
+            col = np.ma.masked_array(vals, mask=np.ma.getmaskarray(col)) if np.ma.isMaskedArray(col) else vals
         if prob:
             col = Dirac(col)                               # predictprob = Dirac(predict) (nn.jl)
     elif isinstance(model, IDW):

@@ -494,8 +494,12 @@ class NNModel:
 
 
 def nn_predict(X: np.ndarray, z: np.ndarray, x0: np.ndarray) -> float:
+    """nn (nn.jl:47-54): values sorted by distance, the first one that is not `missing` (NaN here); NaN when every
+    value is missing."""
     d2 = sqdist_keys(X, x0)
-    return float(z[np.lexsort((np.arange(X.shape[0]), d2))[0]])
+    zs = z[np.lexsort((np.arange(X.shape[0]), d2))]
+    have = np.flatnonzero(~np.isnan(zs))
+    return float(zs[have[0]]) if len(have) else float("nan")
 
 
 def block_offsets(sides, vrange: float) -> np.ndarray:
