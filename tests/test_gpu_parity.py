@@ -788,3 +788,31 @@ def test_nn_model_matches_oracle(gsm, oracle):
         got = gsm.fitpredict(gsm.NN(), gsm.georef({"z": z}, gsm.PointSet(X)), gsm.PointSet(P)).z
         ref, _, _ = o.fitpredict(o.NNModel(), X, z, P, neighbors=False)
         assert np.array_equal(got, ref)
+
+
+def test_translation_invariance_and_covariance_functions(gsm):
+    """test/krig.jl:56-75 (Kriging is translation-invariant) and 314-346 (a covariance function gives the distribution
+    of its variogram), through fit / predictprob on the CUDA path, plus the same through fitpredict with neighbours."""
+    rng = np.random.default_rng(2024)
+    P = rng.uniform(0, 1, size=(100, 3)) * 10.0
+    zz = rng.uniform(size=100)
+    p0 = np.array([5.0, 5.0, 5.0])
+    h = rng.uniform(0, 1, size=3)
+    gam, cov = gsm.GaussianVariogram(sill=1.0, range=1.0, nugget=0.0), gsm.GaussianCovariance(sill=1.0, range=1.0, nugget=0.0)
+    mk = (lambda f: gsm.SimpleKriging(f, float(zz.mean())), gsm.OrdinaryKriging, lambda f: gsm.UniversalKriging(f, 1, 3),
+          lambda f: gsm.UniversalKriging(f, exps=((0, 0, 0),)))
+    for make in mk:
+        d = gsm.predictprob(gsm.fit(make(gam), gsm.georef({"z": zz}, gsm.PointSet(P))), "z", p0)
+        dh = gsm.predictprob(gsm.fit(make(gam), gsm.georef({"z": zz}, gsm.PointSet(P + h))), "z", p0 + h)
+        dc = gsm.predictprob(gsm.fit(make(cov), gsm.georef({"z": zz}, gsm.PointSet(P))), "z", p0)
+        assert dh.mu == pytest.approx(d.mu, rel=1e-8, abs=1e-10) and dh.sigma == pytest.approx(d.sigma, rel=1e-8)
+        assert dc.mu == d.mu and dc.sigma == d.sigma
+    X, z = _samples(78, 5000, 2, 100.0)
+    fun = gsm.SphericalVariogram(range=30.0, sill=1.2, nugget=0.1)
+    grid = gsm.CartesianGrid((0.0, 0.0), (100.0, 100.0), dims=(32, 24))
+    shift = np.array([13.25, -7.5])
+    gridh = gsm.CartesianGrid(tuple(shift), tuple(shift + 100.0), dims=(32, 24))
+    for model in (gsm.OrdinaryKriging(fun), gsm.UniversalKriging(fun, 2, 2)):
+        a = gsm.fitpredict(model, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=24, prob=True).z
+        b = gsm.fitpredict(model, gsm.georef({"z": z}, gsm.PointSet(X + shift)), gridh, maxneighbors=24, prob=True).z
+        assert np.allclose(a.mu, b.mu, rtol=1e-8, atol=1e-10) and np.allclose(a.sigma, b.sigma, rtol=1e-8, atol=1e-10)
