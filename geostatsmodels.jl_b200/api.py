@@ -806,10 +806,11 @@ def predictprob(fitted, var, g):
         d = Dirac(float(mean[0]))
         return d if scalar else [d]
     mean, var_ = _krige_at(fitted, t, block, True)
+    if not scalar:                                        # a tuple of variables: MvNormal(mu, Sigma), krig.jl:231-237
+        return MvNormal([float(mean[0])], [[float(var_[0])]])
     if var_[0] < 0:
         raise ValueError("DomainError: sqrt of negative variance")  # krig.jl:228
-    d = Normal(float(mean[0]), math.sqrt(float(var_[0])))
-    return d if scalar else [d]
+    return Normal(float(mean[0]), math.sqrt(float(var_[0])))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -816,3 +816,29 @@ def test_translation_invariance_and_covariance_functions(gsm):
         a = gsm.fitpredict(model, gsm.georef({"z": z}, gsm.PointSet(X)), grid, maxneighbors=24, prob=True).z
         b = gsm.fitpredict(model, gsm.georef({"z": z}, gsm.PointSet(X + shift)), gridh, maxneighbors=24, prob=True).z
         assert np.allclose(a.mu, b.mu, rtol=1e-8, atol=1e-10) and np.allclose(a.sigma, b.sigma, rtol=1e-8, atol=1e-10)
+
+
+def test_fallback_methods_and_cokriging_on_a_grid(gsm):
+    """test/krig.jl:431-449 (Symbol / String / tuple forms of predict and predictprob) and the CoKriging block of
+    test/misc.jl:27-58 (fitpredict of three variables on a 100 x 100 grid, neighbours on)."""
+    d = gsm.georef({"z": np.array([1.0, 0.0, 1.0])}, [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0)])
+    ok = gsm.fit(gsm.OrdinaryKriging(gsm.GaussianVariogram()), d)
+    p1, p3 = gsm.predict(ok, "z", (0.0, 0.0)), gsm.predict(ok, ("z",), (0.0, 0.0))
+    p4, p6 = gsm.predictprob(ok, "z", (0.0, 0.0)), gsm.predictprob(ok, ("z",), (0.0, 0.0))
+    assert isinstance(p1, float) and isinstance(p3, list) and p1 == p3[0]
+    assert isinstance(p4, gsm.Normal) and isinstance(p6, gsm.MvNormal)
+    assert p6.mean()[0] == p4.mu and p6.var()[0] == pytest.approx(p4.sigma ** 2, rel=1e-12)
+    B = np.array([[1.0, 0.3, 0.1], [0.3, 1.0, 0.2], [0.1, 0.2, 1.0]])
+    model = gsm.Kriging(gsm.CoregionalizedVariogram(B, gsm.SphericalVariogram(range=35.0)))
+    data = gsm.georef({"a": np.array([1.0, 0.0, 0.0]), "b": np.array([0.0, 1.0, 0.0]), "c": np.array([0.0, 0.0, 1.0])},
+                      [(25.0, 25.0), (50.0, 75.0), (75.0, 50.0)])
+    grid = gsm.CartesianGrid((0.5, 0.5), (100.5, 100.5), dims=(100, 100))
+    at = {(25, 25): (1.0, 0.0, 0.0), (50, 75): (0.0, 1.0, 0.0), (75, 50): (0.0, 0.0, 1.0)}
+    for prob in (False, True):
+        pred = gsm.fitpredict(model, data, grid, neighbors=True, prob=prob)
+        assert pred.geometry == grid
+        for (i, j), want in at.items():
+            lin = (i - 1) + (j - 1) * 100          # LinearIndices(size(grid))[i, j], 0-based
+            for name, w in zip(("a", "b", "c"), want):
+                col = pred.table[name]
+                assert abs((col.mu if prob else col)[lin] - w) < 1e-3
