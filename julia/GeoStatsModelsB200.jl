@@ -20,6 +20,8 @@
 module GeoStatsModelsB200
 
 using GeoStatsModels, GeoStatsFunctions, Meshes, GeoTables, Tables, Distributions, Distances
+using LinearAlgebra: I
+using Unitful: ustrip
 import GeoStatsModels: fitpredictneigh, fitpredictfull, SimpleKriging, OrdinaryKriging, UniversalKriging, IDW, NN
 
 const LIB = get(ENV, "GSM_B200_LIB", "libgsm_b200.so")
