@@ -47,6 +47,13 @@ def test_proportional_cokriging_decouples_on_the_oracle(oracle):
                 assert abs(mu1 - mu[p_]) < 1e-10 and abs(var1 - var[p_]) < 1e-10
 
 
+def test_mvnormal_host_class(gsm):
+    d = gsm.MvNormal([1.0, 2.0], [[2.0, 0.3], [0.3, 1.0]])
+    assert list(d.mean()) == [1.0, 2.0] and list(d.var()) == [2.0, 1.0] and d.cov().shape == (2, 2)
+    with pytest.raises(np.linalg.LinAlgError):       # PosDefException of MvNormal(mu, Sigma), krig.jl:236
+        gsm.MvNormal([0.0, 0.0], [[1.0, 2.0], [2.0, 1.0]])
+
+
 @pytest.mark.gpu
 def test_cokriging_gpu_matches_full_system(gsm, oracle):
     o = oracle

@@ -14,6 +14,25 @@ def test_oracle_nn_skips_missing(oracle):
     assert oracle.nn_predict(X, np.array([1.0, 2.0, 3.0]), np.array([0.4, 0.0])) == 1.0
 
 
+def test_value_encoding_and_default_domain(gsm):
+    """host logic: category codes / missing markers, georef without a domain, centroids of grid data"""
+    api = __import__("gsm_b200.api", fromlist=["_encode"])
+    z, cats = api._encode(["b", None, "a", "b"])
+    assert list(cats) == ["a", "b"] and np.array_equal(z, [1.0, np.nan, 0.0, 1.0], equal_nan=True)
+    z, cats = api._encode([1, None, 2.5])
+    assert cats is None and np.array_equal(z, [1.0, np.nan, 2.5], equal_nan=True)
+    z, cats = api._encode(np.ma.masked_array([1.0, 2.0], mask=[False, True]))
+    assert cats is None and z[0] == 1.0 and np.isnan(z[1])
+    d = gsm.georef({"z": ["a", "b", "c"]})
+    assert d.domain == gsm.CartesianGrid(3)
+    assert np.array_equal(api._pointset_of(d.domain, centroids_ok=True), [[0.5], [1.5], [2.5]])
+    g = gsm.CartesianGrid((0.0, 10.0), (4.0, 16.0), dims=(2, 3))
+    assert np.array_equal(api._pointset_of(g, centroids_ok=True),
+                          [[1.0, 11.0], [3.0, 11.0], [1.0, 13.0], [3.0, 13.0], [1.0, 15.0], [3.0, 15.0]])
+    with pytest.raises(NotImplementedError):
+        api._pointset_of(g)
+
+
 @pytest.mark.gpu
 def test_nn_basics_reference_testset(gsm):
     data = gsm.georef({"z": ["a", "b", "c"]})                       # test/nn.jl:3-10: cells of CartesianGrid(3)
