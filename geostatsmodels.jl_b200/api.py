@@ -779,6 +779,8 @@ def predict(fitted, var, g):
     t, block = _target_of(fitted, g)
     if isinstance(fitted, FittedIDW):
         mean, _ = fitted._ctx.idw(fitted.model.exponent, t)
+        if mean[0] != mean[0]:                          # a `missing` value among the samples (idw.jl:59-73)
+            return None if scalar else [None]
     else:
         mean, _ = _krige_at(fitted, t, block, False)
     return float(mean[0]) if scalar else [float(mean[0])]
@@ -939,8 +941,8 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             floor = max(floor, float(np.abs(X).max()))
             kmodel, X, z = _drop_missing(model, X, z)
         alpha, nnan = ctx.set_samples_scaled(X, z, floor)
-    if nnan and not (isinstance(model, _KrigingModel) and neighbors):
-        raise NotImplementedError("missing values are claimed for Kriging models only")
+    if nnan and not ((isinstance(model, _KrigingModel) and neighbors) or isinstance(model, IDW)):
+        raise NotImplementedError("missing values are claimed for Kriging models, IDW and global NN only")
     out = out or {}
     t = _targets_for(dom, alpha, first, count)
     radius = 0.0
@@ -972,6 +974,11 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
         else:
             mean, st = ctx.idw(model.exponent, t)
         col = _mask_missing(mean, st)
+        if nnan:
+            # a `missing` value among the weighted samples makes the sum `missing` (idw.jl:59-73): NaN on the device
+            nanmask = np.isnan(np.ma.getdata(col))
+            if nanmask.any():
+                col = np.ma.masked_array(np.ma.getdata(col), mask=nanmask | np.ma.getmaskarray(col))
         if prob:
             col = Dirac(col)                               # predictprob = Dirac(predict) (idw.jl:57)
     else:

@@ -595,10 +595,9 @@ static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, co
       return GSM_ERR_INVALID;
     }
   }
-  if (ctx->n_missing > 0 && mode == 2) {
-    gsm_set_error(ctx, "IDW with missing values is not claimed by the GPU path");
-    return GSM_ERR_UNSUPPORTED;
-  }
+  // (IDW with missing values needs no branch: a NaN value makes the weighted sum NaN, which is the reference's
+  //  `missing` from sum(i -> w_i z_i) over a column with missings, and an exact hit returns that sample's value
+  //  whatever the others hold, idw.jl:59-73)
   int maxn, minn;
   clamp_neighbors(ctx->n, opts, maxn, minn);
   if (maxn > GSM_MAX_NEIGHBORS) {

@@ -108,3 +108,32 @@ def test_dirac_and_nn_ball(gsm, oracle):
     d2 = ((T[:, None, :] - X[None, :, :]) ** 2).sum(-1)
     inside = (np.sqrt(d2) <= 1.0).sum(1)
     assert np.array_equal(np.ma.getmaskarray(c), np.minimum(inside, 5) < 2)
+
+
+def test_idw_with_missing_values(gsm, oracle):
+    """idw.jl:59-73 on a column with `missing`: the weighted sum over samples that include a missing value is `missing`;
+    an exact hit returns that sample's value (missing or not) whatever the other samples hold."""
+    o = oracle
+    rng = np.random.default_rng(17)
+    X = rng.uniform(0, 30, size=(2000, 2))
+    z = np.sin(X[:, 0] / 5) + 0.1 * rng.standard_normal(2000)
+    z[rng.random(2000) < 0.02] = np.nan
+    P = np.concatenate([rng.uniform(0, 30, size=(400, 2)), X[:40]])          # 40 exact hits, some on missing samples
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    got = gsm.fitpredict(gsm.IDW(2), tab, gsm.PointSet(P), maxneighbors=8)
+    ref, _, st = o.fitpredict(o.IDWModel(2), X, z, P, maxneighbors=8)
+    col = got.z
+    assert np.ma.isMaskedArray(col) and np.array_equal(np.ma.getmaskarray(col), np.isnan(ref))
+    assert 0 < np.isnan(ref).sum() < len(ref)
+    assert np.allclose(np.ma.getdata(col)[~np.isnan(ref)], ref[~np.isnan(ref)], rtol=1e-12, atol=1e-13)
+    hits = np.ma.getdata(col)[400:]
+    assert np.array_equal(np.isnan(z[:40]), np.ma.getmaskarray(col)[400:]) and np.array_equal(hits[~np.isnan(z[:40])], z[:40][~np.isnan(z[:40])])
+    # all samples (neighbors=false): every prediction away from a sample with a value is missing
+    got = gsm.fitpredict(gsm.IDW(1), tab, gsm.PointSet(P), neighbors=False).z
+    ref, _, _ = o.fitpredict(o.IDWModel(1), X, z, P, neighbors=False)
+    assert np.array_equal(np.ma.getmaskarray(got), np.isnan(ref)) and np.isnan(ref[:400]).all()
+    assert np.array_equal(np.ma.getdata(got)[~np.isnan(ref)], ref[~np.isnan(ref)])
+    f = gsm.fit(gsm.IDW(1), tab)
+    assert gsm.predict(f, "z", P[0]) is None
+    j = int(np.flatnonzero(~np.isnan(z[:40]))[0])
+    assert gsm.predict(f, "z", X[j]) == z[j]
