@@ -289,16 +289,19 @@ function idwcall(model::IDW, dat, dom, opts, prob)
   GC.@preserve keep mean status check(h, ccall((h.multi ? :gsm_multi_idw : :gsm_idw, LIB), Cint,
     (Ptr{Cvoid}, Float64, Ref{GsmTargets}, Ptr{GsmNeighborOpts}, Ptr{Float64}, Ptr{UInt8}),
     h.ptr, Float64(model.exponent), Ref(tg), opts === nothing ? C_NULL : Ref(opts), mean, status))
-  col = any(==(0x01), status) ? [s == 1 ? missing : (prob ? Dirac(mean[i]) : mean[i]) for (i, s) in enumerate(status)] :
+  # a `missing` among the weighted values makes the sum `missing` (idw.jl:59-73): NaN on the device
+  gone(i, s) = s == 1 || isnan(mean[i])
+  col = (any(==(0x01), status) || any(ismissing, column(dat))) ?
+        [gone(i, s) ? missing : (prob ? Dirac(mean[i]) : mean[i]) for (i, s) in enumerate(status)] :
         (prob ? Dirac.(mean) : mean)                         # predictprob = Dirac(predict) (idw.jl:57)
   (; var => col) |> Tables.materializer(values(dat))
 end
 function fitpredictfull(model::IDW{<:Real,<:Euclidean}, dat, dom, point, prob)
-  (claimed(dat, dom, point, model.distance) && !any(ismissing, column(dat))) || return generic_full(model, dat, dom, point, prob)
+  claimed(dat, dom, point, model.distance) || return generic_full(model, dat, dom, point, prob)
   idwcall(model, dat, dom, nothing, prob)
 end
 function fitpredictneigh(model::IDW{<:Real,<:Euclidean}, dat, dom, point, prob, minneighbors, maxneighbors, neighborhood, distance)
-  (claimed(dat, dom, point, distance) && !any(ismissing, column(dat)) && clampmax(maxneighbors, nrow(dat)) <= MAXK &&
+  (claimed(dat, dom, point, distance) && clampmax(maxneighbors, nrow(dat)) <= MAXK &&
    (neighborhood === nothing || neighborhood isa MetricBall)) ||
     return generic_neigh(model, dat, dom, point, prob, minneighbors, maxneighbors, neighborhood, distance)
   idwcall(model, dat, dom, GsmNeighborOpts(maxneighbors, minneighbors, neighborhood === nothing ? 0.0 : ustrip(radius(neighborhood))), prob)
