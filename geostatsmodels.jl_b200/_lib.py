@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "gsm_abi_version", "gsm_create", "gsm_destroy", "gsm_last_error", "gsm_get_timings", "gsm_get_summary", "gsm_synchronize",
     "gsm_host_alloc", "gsm_host_free", "gsm_set_samples", "gsm_set_samples_scaled", "gsm_knn", "gsm_local_krige",
     "gsm_global_krige_fit", "gsm_global_krige_status", "gsm_global_krige_predict", "gsm_global_krige_free",
-    "gsm_idw", "gsm_nn", "gsm_measure_fp64_peak", "gsm_set_option", "gsm_set_block_support",
+    "gsm_idw", "gsm_nn", "gsm_nn_local", "gsm_measure_fp64_peak", "gsm_set_option", "gsm_set_block_support",
     "gsm_multi_create", "gsm_multi_destroy", "gsm_multi_last_error", "gsm_multi_device_count", "gsm_multi_context",
     "gsm_multi_get_timings", "gsm_multi_get_summary", "gsm_multi_set_samples", "gsm_multi_set_samples_scaled",
     "gsm_multi_slab", "gsm_multi_local_krige", "gsm_multi_idw", "gsm_multi_global_krige",
@@ -125,6 +125,7 @@ def load():
     lib.gsm_global_krige_free.argtypes = [vp]
     lib.gsm_idw.argtypes = [vp, dbl, P(Targets), P(NeighborOpts), vp, vp]
     lib.gsm_nn.argtypes = [vp, P(Targets), vp]
+    lib.gsm_nn_local.argtypes = [vp, P(Targets), P(NeighborOpts), vp, vp]
     lib.gsm_measure_fp64_peak.argtypes = [vp, P(dbl), P(dbl)]
     lib.gsm_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     lib.gsm_set_block_support.argtypes = [vp, C.c_void_p, C.c_int32, C.c_int32]
@@ -406,6 +407,15 @@ class Context:
         val = _pool.empty(M, np.float64) if out is None else out
         self._check(self._lib.gsm_nn(self._h, C.byref(targets), _ptr(val)))
         return val
+
+    def nn_local(self, targets: Targets, maxneighbors: int, minneighbors: int = 1, radius: float = 0.0, out=None):
+        """nearest sample WITH a value among the maxneighbors nearest (gsm_nn_local); status 1 = `missing`"""
+        M = self.target_count(targets)
+        val = _pool.empty(M, np.float64) if out is None else out
+        status = _pool.empty(M, np.uint8)
+        o = NeighborOpts(int(maxneighbors), int(minneighbors), float(radius))
+        self._check(self._lib.gsm_nn_local(self._h, C.byref(targets), C.byref(o), _ptr(val), _ptr(status)))
+        return val, status
 
     def global_fit(self, vario: Variogram, model: Model):
         h = C.c_void_p()

@@ -941,8 +941,8 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             floor = max(floor, float(np.abs(X).max()))
             kmodel, X, z = _drop_missing(model, X, z)
         alpha, nnan = ctx.set_samples_scaled(X, z, floor)
-    if nnan and not ((isinstance(model, _KrigingModel) and neighbors) or isinstance(model, IDW)):
-        raise NotImplementedError("missing values are claimed for Kriging models, IDW and global NN only")
+    if nnan and not ((isinstance(model, (_KrigingModel, NN)) and neighbors) or isinstance(model, IDW)):
+        raise NotImplementedError("missing values are not claimed for this model / option combination")
     out = out or {}
     t = _targets_for(dom, alpha, first, count)
     radius = 0.0
@@ -954,8 +954,14 @@ def fitpredict(model, data: GeoTable, dom, *, point=True, prob=False, neighbors=
             raise NotImplementedError("NN is served by the single-device context")
         # nearest of the k nearest = nearest of all (nn.jl:47-54) -- unless a ball neighbourhood leaves fewer than
         # minneighbors samples inside the ball: that target is `missing` (models.jl:167-181)
-        col = ctx.nn(t, out=out.get("mean"))
-        if neighbors and neighborhood is not None:
+        if neighbors and nnan:
+            # a column with missings behind a neighbour search: the nearest of the k nearest that HAS a value, `missing`
+            # when none has (models.jl:162-184 with nn.jl:47-54)
+            col, st = ctx.nn_local(t, _clamp_max(maxneighbors, nobs), minneighbors, radius, out=out.get("mean"))
+            col = _mask_missing(col, st)
+        else:
+            col = ctx.nn(t, out=out.get("mean"))
+        if neighbors and neighborhood is not None and not nnan:
             _, cnt = ctx.knn(t, _clamp_max(maxneighbors, nobs), radius)
             kmax = _clamp_max(maxneighbors, nobs)
             minn = 1 if (minneighbors > kmax or minneighbors < 1) else minneighbors

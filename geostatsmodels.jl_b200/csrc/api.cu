@@ -581,7 +581,7 @@ static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, co
     return GSM_ERR_INVALID;
   }
   DeviceGuard g(ctx->device);
-  GsmRange nv(mode == 0 ? "gsm_knn" : (mode == 1 ? "gsm_local_krige" : "gsm_idw (local)"));
+  GsmRange nv(mode == 0 ? "gsm_knn" : (mode == 1 ? "gsm_local_krige" : (mode == 2 ? "gsm_idw (local)" : "gsm_nn_local")));
   ctx->tim = gsm_timings{};
   VarioDev vd{};
   ModelDev md{};
@@ -692,6 +692,8 @@ static int run_local_body(gsm_ctx* ctx, int mode, const gsm_variogram* vario, co
       GSM_CHECK(gsm_launch_idw_local(ctx, exponent, tc, maxn, minn, d_pos, d_cnt, omean.dev + off,
                                      ostat.dev ? ostat.dev + off : nullptr));
     }
+    if (mode == 3)
+      GSM_CHECK(gsm_launch_nn_local(ctx, tc, maxn, minn, d_pos, d_cnt, omean.dev + off, ostat.dev ? ostat.dev + off : nullptr));
     cudaEvent_t c = et.mark(st);
     if (mode != 0 && ostat.dev) {   // (after the solve mark: not part of solve_ms)
       summary_kernel<<<(unsigned)((tc.count + 255) / 256), 256, 0, st>>>(ostat.dev + off, ovar.dev ? ovar.dev + off : nullptr,
@@ -786,6 +788,15 @@ int gsm_nn(gsm_ctx* ctx, const gsm_targets* targets, double* out_value) {
   ctx->tim.d2h_ms = EventTimer::ms(e2, e3);
   ctx->tim.total_ms = EventTimer::ms(e0, e3);
   return GSM_OK;
+}
+
+int gsm_nn_local(gsm_ctx* ctx, const gsm_targets* targets, const gsm_neighbor_opts* opts, double* out_value,
+                 uint8_t* out_status) {
+  if (ctx && !out_value) {
+    gsm_set_error(ctx, "out_value is required");
+    return GSM_ERR_INVALID;
+  }
+  return run_local(ctx, 3, nullptr, nullptr, 0.0, targets, opts, out_value, nullptr, out_status, nullptr, nullptr);
 }
 
 int gsm_idw(gsm_ctx* ctx, double exponent, const gsm_targets* targets, const gsm_neighbor_opts* opts,

@@ -233,6 +233,8 @@ int gsm_launch_knn(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, int
 int gsm_launch_knn_idw(gsm_ctx* ctx, const TargetsDev& tg, int k, double radius, double exponent, int minneighbors,
                        int* d_cnt, double* d_mean, unsigned char* d_status);
 int gsm_launch_knn_nearest(gsm_ctx* ctx, const TargetsDev& tg, int* d_cnt, double* d_value);
+int gsm_launch_nn_local(gsm_ctx* ctx, const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                        double* d_val, unsigned char* d_status);
 int gsm_launch_sort_lists(gsm_ctx* ctx, const TargetsDev& tg, int k, int* d_pos, const int* d_cnt);
 int gsm_launch_nbr_to_rows(gsm_ctx* ctx, const int* d_pos, long long total, int* d_rows);
 int gsm_launch_local_krige(gsm_ctx* ctx, const VarioDev& v, const ModelDev& m, const TargetsDev& tg, int k,

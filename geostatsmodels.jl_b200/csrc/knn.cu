@@ -564,6 +564,50 @@ int gsm_launch_knn_nearest(gsm_ctx* ctx, const TargetsDev& tg, int* d_cnt, doubl
   return launch_knn_impl(ctx, tg, 1, 0.0, f, nullptr, d_cnt);
 }
 
+namespace {
+// NN over a neighbour list (fitpredictneigh with the NN model, models.jl:162-184 + nn.jl:47-54): the nearest, in the
+// order (d2, row), of the selected samples that has a value; `missing` when fewer than minneighbors were found or none
+// of them has a value.
+__global__ void nn_local_kernel(BinsDev b, TargetsDev tg, int k, int minn, const int* __restrict__ pos,
+                                const int* __restrict__ cnt, double* __restrict__ out, unsigned char* __restrict__ status) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= tg.count) return;
+  const int n = cnt[t];
+  double tx, ty, tz;
+  gsm_target_coords(tg, tg.first + t, tx, ty, tz);
+  const int* p = pos + t * (long long)k;
+  double best = 0.0, val = __longlong_as_double(0x7ff8000000000000LL);
+  int brow = 0x7fffffff;
+  bool found = false;
+  if (n >= minn)
+    for (int i = 0; i < n; ++i) {
+      const int q = p[i];
+      const double4 r = b.rec[q];
+      if (r.w != r.w) continue;   // no value
+      const double d2 = gsm_d2_key(r.x, r.y, r.z, tx, ty, tz);
+      const int rw = b.sidx[q];
+      if (!found || d2 < best || (d2 == best && rw < brow)) {
+        found = true;
+        best = d2;
+        brow = rw;
+        val = r.w;
+      }
+    }
+  out[t] = val;
+  if (status) status[t] = found ? GSM_ST_OK : GSM_ST_MISSING;
+}
+}  // namespace
+
+int gsm_launch_nn_local(gsm_ctx* ctx, const TargetsDev& tg, int k, int minneighbors, const int* d_pos, const int* d_cnt,
+                        double* d_val, unsigned char* d_status) {
+  if (tg.count <= 0) return GSM_OK;
+  nn_local_kernel<<<(unsigned)((tg.count + 127) / 128), 128, 0, ctx->stream>>>(ctx->bins, tg, k, minneighbors, d_pos, d_cnt,
+                                                                             d_val, d_status);
+  ctx->tim.launches++;
+  GSM_CUDA(ctx, cudaGetLastError());
+  return GSM_OK;
+}
+
 int gsm_launch_sort_lists(gsm_ctx* ctx, const TargetsDev& tg, int k, int* d_pos, const int* d_cnt) {
   if (tg.count <= 0) return GSM_OK;
   sort_lists_kernel<<<(unsigned)((tg.count + 127) / 128), 128, 0, ctx->stream>>>(ctx->bins, tg, k, d_pos, d_cnt);

@@ -228,6 +228,12 @@ GSM_API int gsm_idw(gsm_ctx* ctx, double exponent, const gsm_targets* targets, c
 /* ---- NN (nn.jl:47-54): value of the nearest sample (ties: the lowest sample row, the order a stable sortperm of the
  * distances gives).  SURVEY section 8(f) "next" row; missing values are not claimed. */
 GSM_API int gsm_nn(gsm_ctx* ctx, const gsm_targets* targets, double* out_value);
+/* The NN model behind a neighbour search: per-target body of fitpredictneigh (/root/reference/src/models.jl:162-184)
+ * with fit / predict of src/nn.jl:30-54 -- the nearest of the maxneighbors nearest samples (inside the ball when
+ * opts->radius > 0) THAT HAS A VALUE (NaN = `missing` is skipped, nn.jl:51-53); out_status 1 = `missing`: fewer than
+ * minneighbors samples found, or none of them has a value. */
+GSM_API int gsm_nn_local(gsm_ctx* ctx, const gsm_targets* targets, const gsm_neighbor_opts* opts, double* out_value,
+                         uint8_t* out_status);
 
 /* ---- multi-GPU: ONE caller drives all GPUs of a box (reference analogue: the contiguous
  * index chunks of `_predictionthread!`, models.jl:236-247, one private fitted state per chunk, no exchange step).

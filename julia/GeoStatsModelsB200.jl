@@ -308,12 +308,22 @@ function fitpredictneigh(model::IDW{<:Real,<:Euclidean}, dat, dom, point, prob, 
 end
 function fitpredictneigh(model::NN{<:Euclidean}, dat, dom, point, prob, minneighbors, maxneighbors, neighborhood, distance)
   h = handle()
-  (claimed(dat, dom, point, distance) && !any(ismissing, column(dat)) && neighborhood === nothing && !h.multi) ||
+  plain = !any(ismissing, column(dat)) && neighborhood === nothing
+  (claimed(dat, dom, point, distance) && !h.multi && (plain || (clampmax(maxneighbors, nrow(dat)) <= MAXK &&
+   (neighborhood === nothing || neighborhood isa MetricBall)))) ||
     return generic_neigh(model, dat, dom, point, prob, minneighbors, maxneighbors, neighborhood, distance)
   setsamples!(h, dat)
   M = nelements(dom); var = first(Tables.columnnames(Tables.columns(values(dat))))
   val = pinned(Float64, M)
   tg, keep = targets(dom)
+  if !plain   # missings or a ball: nearest of the k nearest that has a value, `missing` when none (gsm_nn_local)
+    status = pinned(UInt8, M)
+    o = Ref(GsmNeighborOpts(maxneighbors, minneighbors, neighborhood === nothing ? 0.0 : ustrip(radius(neighborhood))))
+    GC.@preserve keep val status check(h, ccall((:gsm_nn_local, LIB), Cint,
+      (Ptr{Cvoid}, Ref{GsmTargets}, Ref{GsmNeighborOpts}, Ptr{Float64}, Ptr{UInt8}), h.ptr, Ref(tg), o, val, status))
+    col = [s == 1 ? missing : (prob ? Dirac(val[i]) : val[i]) for (i, s) in enumerate(status)]
+    return (; var => col) |> Tables.materializer(values(dat))
+  end
   GC.@preserve keep val check(h, ccall((:gsm_nn, LIB), Cint, (Ptr{Cvoid}, Ref{GsmTargets}, Ptr{Float64}), h.ptr, Ref(tg), val))
   (; var => (prob ? Dirac.(val) : val)) |> Tables.materializer(values(dat))
 end

@@ -79,3 +79,29 @@ def test_nn_fitpredict_categories_missing_and_grid_data(gsm, oracle):
     assert np.allclose(got, ref, rtol=1e-10, atol=1e-12)
     with pytest.raises(NotImplementedError):          # data with volume support under point=false: not claimed
         gsm.fitpredict(ok, gsm.georef({"z": z}, dgrid), grid, maxneighbors=12, point=False)
+
+
+@pytest.mark.gpu
+def test_nn_with_missing_values_behind_a_neighbour_search(gsm, oracle):
+    """fitpredictneigh with NN over a column with `missing` (models.jl:162-184, nn.jl:47-54): nearest of the k nearest
+    that has a value; `missing` when none has, or when the ball holds fewer than minneighbors samples."""
+    o = oracle
+    rng = np.random.default_rng(23)
+    X = rng.uniform(0, 40, size=(4000, 2))
+    z = np.round(rng.standard_normal(4000), 3)
+    z[rng.random(4000) < 0.6] = np.nan                     # most samples have no value
+    grid = gsm.CartesianGrid((0.0, 0.0), (40.0, 40.0), dims=(50, 40))
+    og = o.Grid((0.0, 0.0), (0.8, 1.0), (50, 40))
+    tab = gsm.georef({"z": z}, gsm.PointSet(X))
+    for kw in (dict(maxneighbors=3), dict(maxneighbors=10), dict(maxneighbors=6, minneighbors=4, neighborhood=1.2)):
+        got = gsm.fitpredict(gsm.NN(), tab, grid, **kw).z
+        ref, _, st = o.fitpredict(o.NNModel(), X, z, og, **kw)
+        gone = np.isnan(ref) | (st == 1)
+        assert 0 < gone.sum() < len(ref), kw
+        assert np.array_equal(np.ma.getmaskarray(got), gone), kw
+        assert np.array_equal(np.ma.getdata(got)[~gone], ref[~gone]), kw
+    lab = np.array([None if np.isnan(v) else ("hi" if v > 0 else "lo") for v in z], dtype=object)
+    got = gsm.fitpredict(gsm.NN(), gsm.georef({"z": list(lab)}, gsm.PointSet(X)), grid, maxneighbors=3).z
+    ref, _, _ = o.fitpredict(o.NNModel(), X, np.where(np.isnan(z), np.nan, (z > 0) * 1.0), og, maxneighbors=3)
+    assert np.array_equal(np.ma.getmaskarray(got), np.isnan(ref))
+    assert list(np.ma.getdata(got)[~np.isnan(ref)]) == [("hi" if c == 1.0 else "lo") for c in ref[~np.isnan(ref)]]
