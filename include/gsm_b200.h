@@ -28,6 +28,8 @@ extern "C" {
 #define GSM_API
 #endif
 
+/* 2: nested / anisotropic variogram descriptors, gsm_set_option, the gsm_multi_* family.  Entry points added since
+ * (gsm_set_block_support, gsm_nn_local) do not change any existing layout or signature, so the number stays. */
 #define GSM_ABI_VERSION 2
 #define GSM_MAX_DIM 3
 #define GSM_MAX_DRIFT 10   /* UniversalKriging(fun, deg=2, dim=3) -> 10 monomials (universal.jl:54-77) */
